@@ -1,0 +1,432 @@
+#!/usr/bin/env python3
+"""bench.py -- verify-step throughput of the B200-native speculative-decoding verify path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): verify-step tokens/s at B=64 per GPU, K=4, V=128256 (Llama-3.2 vocabulary),
+bf16 logits, kv_append of the accepted rows for the 28 layers of Llama-3.2-3B (Hkv=8, D=128).
+One step = fused verify over [B, K+1, V] logits + kv_append for all layers (+ the all-gather of the
+packed [B, K+2] records when N > 1), replayed as one CUDA graph.
+tokens/s = (sum_b accept_len[b] + B) / t_step   (accepted drafts + one bonus token per sequence).
+
+The JSON line follows the driver contract and adds `roofline` (dominant kernel: fused verify),
+`roofline_kv` (kv_append), `cpu_baseline` and `e2e`.  See DESIGN.md section "Measurement".
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path[:0] = [str(ROOT / "llm-inference-lab_b200"), str(ROOT)]
+
+import torch  # noqa: E402
+
+METRIC = "verify-step tokens/s (B=64,K=4) at 1/2/4/8 B200; % of HBM roofline"
+UNIT = "tokens/s"
+SEED = 1234  # the reference's default seed (src/specdec/core/pipeline.py:407)
+
+# configs[2] of BASELINE.json: Llama-3.2-3B target (28 layers, 8 KV heads, head_dim 128, V=128256)
+CFG = dict(B=64, K=4, V=128256, layers=28, Hkv=8, D=128, L=1024, p_match=0.8, nbuf=4)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
+    ap.add_argument("--tuning", default="", help="threads,vectors_per_thread for the verify kernel (sweeps)")
+    ap.add_argument("--kv-variant", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=CFG["B"], help="sequences per GPU")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------- inputs
+def make_inputs(B, K, V, p_match, seed, device):
+    """Synthetic inputs per SURVEY.md section 8d: randn -> bf16 logits, randint ids, planted 10.0 with
+    probability p_match (scripts/microbench_verify.py:57-64)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    logits = torch.randn(B, K + 1, V, generator=g, device=device, dtype=torch.float32).to(torch.bfloat16)
+    ids = torch.randint(0, V, (B, K), generator=g, device=device, dtype=torch.int64)
+    plant = torch.rand(B, K, generator=g, device=device) < p_match
+    bi, ki = torch.nonzero(plant, as_tuple=True)
+    logits[bi, ki, ids[bi, ki]] = 10.0
+    return logits, ids
+
+
+# ----------------------------------------------------------------------------------------- reference arm
+def cpu_port_step_time(B, K, V, layers_sample, Hkv, D, L, keep_rows, reps, threads, budget_s=25.0):
+    """Times the reference's CPU arithmetic (oracle/torch_port.py == torch.argmax + host prefix loop,
+    torch.cat per layer) on host cores.  Returns (t_verify, t_kv_per_layer, sample description)."""
+    from oracle import torch_port as P
+
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(SEED)
+    logits = torch.randn(B, K + 1, V, generator=g).to(torch.bfloat16)
+    ids = torch.randint(0, V, (B, K), generator=g)
+    plant = torch.rand(B, K, generator=g) < CFG["p_match"]
+    bi, ki = torch.nonzero(plant, as_tuple=True)
+    logits[bi, ki, ids[bi, ki]] = 10.0
+    base = [(torch.randn(B, Hkv, L, D, generator=g).to(torch.bfloat16), torch.randn(B, Hkv, L, D, generator=g).to(torch.bfloat16))
+            for _ in range(layers_sample)]
+    new = [(torch.randn(B, Hkv, K + 1, D, generator=g).to(torch.bfloat16), torch.randn(B, Hkv, K + 1, D, generator=g).to(torch.bfloat16))
+           for _ in range(layers_sample)]
+    P.verify_step_port(logits, ids)
+    P.kv_append_layers_port(base[:1], new[:1], keep_rows)
+    tv, tk = [], []
+    t_start = time.perf_counter()
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        P.verify_step_port(logits, ids)
+        t1 = time.perf_counter()
+        P.kv_append_layers_port(base, new, keep_rows)
+        t2 = time.perf_counter()
+        tv.append(t1 - t0)
+        tk.append((t2 - t1) / layers_sample)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    tv.sort()
+    tk.sort()
+    return tv[len(tv) // 2], tk[len(tk) // 2], len(tv)
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (torch-on-CPU port, all host
+    threads), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    B, K, V = args.batch, CFG["K"], CFG["V"]
+    layers_sample = 2
+    keep_rows = 4  # mean rows kept at p_match 0.8 is ~3.7; the reference appends a uniform slice
+    n = max(1, min(args.steps + args.warmup, 8))
+    tv, tk, reps = cpu_port_step_time(B, K, V, layers_sample, CFG["Hkv"], CFG["D"], CFG["L"], keep_rows, n, cores,
+                                      budget_s=150.0)
+    t_step = tv + tk * CFG["layers"]
+    mean_tokens = B * (1 + expected_accept(CFG["p_match"], K))
+    value = mean_tokens / t_step
+    sample = (f"median of {reps} steps: verify_prefix+bonus port on full [B={B},K+1={K + 1},V={V}] bf16 logits; "
+              f"kv_append_ref (torch.cat, L={CFG['L']}, {keep_rows} rows) timed on {layers_sample} of {CFG['layers']} layers "
+              f"and scaled to {CFG['layers']}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "verify_ms": tv * 1e3, "kv_append_ms_per_layer": tk * 1e3},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def expected_accept(p, K):
+    return sum(p ** i for i in range(1, K + 1))
+
+
+def workload_config(args, world):
+    return {
+        "workload": "Llama-3.2-3B target verify step (BASELINE configs[2]): fused verify over [B,K+1,V] bf16 logits "
+                    "+ kv_append of accepted rows, 28 layers x 8 KV heads x 128",
+        "batch_per_gpu": args.batch, "global_batch": args.batch * world, "K": CFG["K"], "V": CFG["V"],
+        "layers": CFG["layers"], "kv_heads": CFG["Hkv"], "head_dim": CFG["D"], "context_len": CFG["L"],
+        "planted_acceptance": CFG["p_match"], "parallelism": f"batch-sharded dp{world}",
+        "l2_policy": f"inputs rotate over {CFG['nbuf']} buffer sets ({CFG['nbuf']} x 82 MB logits + {CFG['nbuf']} x 73 MB KV rows "
+                     "> 126 MB L2) so every replay reads from HBM",
+    }
+
+
+# ----------------------------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch.distributed as dist
+
+    from kernels import cuda_ops
+    from scheduler.batch_shard import BatchShard, StepResultExchange
+    from specdec.cache.kv_arena import KVArena
+    from specdec.verify_step import VerifyStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the sd_b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.tuning:
+        t, v = (int(x) for x in args.tuning.split(","))
+        cuda_ops.set_verify_tuning(t, v)
+    if args.kv_variant:
+        cuda_ops.set_kv_variant(args.kv_variant)
+
+    B, K, V, NB = args.batch, CFG["K"], CFG["V"], CFG["nbuf"]
+    R = K + 1
+    total_steps = args.steps + args.warmup
+    e2e_steps = 0 if args.no_e2e else max(3, min(args.steps, 20))
+    capacity = CFG["L"] + R * (2 * total_steps + 2 * NB + e2e_steps + 16)
+    arena = KVArena(CFG["layers"], B, CFG["Hkv"], CFG["D"], capacity, R, torch.bfloat16, dev)
+    arena.set_lengths([CFG["L"]] * B)
+
+    # NB rotating input sets; each set has its own VerifyStep (static buffers) sharing one arena
+    steps, stage_k, stage_v = [], [], []
+    g = torch.Generator(device=dev).manual_seed(SEED + rank)
+    for i in range(NB):
+        st = VerifyStep(B, K, V, arena=None, device=dev)
+        lg, ids = make_inputs(B, K, V, CFG["p_match"], SEED + 17 * rank + i, dev)
+        st.logits.copy_(lg)
+        st.draft_ids.copy_(ids)
+        del lg
+        steps.append(st)
+        stage_k.append(torch.randn(arena.new_k.shape, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16))
+        stage_v.append(torch.randn(arena.new_v.shape, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16))
+    tables = [arena._build_table(stage_k[i], stage_v[i]) for i in range(NB)]
+    shard = BatchShard(B * world, world, rank)
+    exch = StepResultExchange(shard, K, dev) if world > 1 else None
+
+    def one_step(i):
+        st = steps[i]
+        st.run()
+        arena.layer_table = tables[i]
+        arena.append(st.accept_len, keep_bias=1, zero_rejected=True, check_capacity=False)
+        if exch is not None:
+            exch.all_gather(st.packed)
+
+    # warm every buffer set eagerly, then capture one graph per set
+    for i in range(NB):
+        one_step(i)
+    torch.cuda.synchronize()
+    graphs = []
+    side = torch.cuda.Stream(dev)
+    with torch.cuda.stream(side):
+        for i in range(NB):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=side):
+                one_step(i)
+            graphs.append(gr)
+    torch.cuda.synchronize()
+    arena.set_lengths([CFG["L"]] * B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(args.warmup):
+        graphs[s % NB].replay()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for s in range(args.steps):
+        graphs[s % NB].replay()
+    ev1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = ev0.elapsed_time(ev1) / args.steps
+
+    # ---- kernel-isolation loops for the roofline (same buffers, same rotation, CUDA events) ----
+    def isolate(fn, n_launch):
+        grs = []
+        with torch.cuda.stream(side):
+            for i in range(NB):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=side):
+                    fn(i)
+                grs.append(gr)
+        torch.cuda.synchronize()
+        for s in range(max(3, args.warmup)):
+            grs[s % NB].replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for s in range(n_launch):
+            grs[s % NB].replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n_launch
+
+    def kv_only(i):
+        arena.layer_table = tables[i]
+        arena.append(steps[i].accept_len, keep_bias=1, zero_rejected=True, check_capacity=False)
+
+    verify_ms = isolate(lambda i: steps[i].run(), args.steps)
+    arena.set_lengths([CFG["L"]] * B)
+    kv_ms = isolate(kv_only, args.steps)
+    clocks = sampler.stop()
+
+    acc_sum = [int(steps[i].accept_len.sum().item()) for i in range(NB)]
+    tokens_per_step = sum(acc_sum[s % NB] + B for s in range(args.steps)) / args.steps
+    mean_keep = sum(a + B for a in acc_sum) / (NB * B)
+    assert int(arena.overflow.item()) == 0, "KV arena overflowed during the bench"
+
+    # ---- e2e: host buffers in, packed record out, copies inside the timed region ----
+    e2e = None
+    if e2e_steps:
+        arena.set_lengths([CFG["L"]] * B)
+        h_logits = [steps[i].logits.cpu().pin_memory() for i in range(2)]
+        h_ids = [steps[i].draft_ids.cpu().pin_memory() for i in range(2)]
+        h_k = [stage_k[i].cpu().pin_memory() for i in range(2)]
+        h_v = [stage_v[i].cpu().pin_memory() for i in range(2)]
+        h_out = torch.empty((B, K + 2), dtype=torch.int32).pin_memory()
+        h2d = h_logits[0].numel() * 2 + h_ids[0].numel() * 8 + 2 * h_k[0].numel() * 2
+        d2h = h_out.numel() * 4
+
+        def e2e_step(s):
+            i = s % 2
+            steps[0].logits.copy_(h_logits[i], non_blocking=True)
+            steps[0].draft_ids.copy_(h_ids[i], non_blocking=True)
+            stage_k[0].copy_(h_k[i], non_blocking=True)
+            stage_v[0].copy_(h_v[i], non_blocking=True)
+            graphs[0].replay()
+            h_out.copy_(steps[0].packed, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller needs the record to advance sequences
+            return int(h_out[:, 0].sum()) + B
+
+        for s in range(3):
+            e2e_step(s)
+        barrier()
+        t0 = time.perf_counter()
+        toks = 0
+        for s in range(e2e_steps):
+            toks += e2e_step(s)
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        e2e = {"tokens": toks, "seconds": t_e2e, "h2d": h2d, "d2h": d2h}
+
+    # ---- reduce over ranks: max time, summed tokens ----
+    if world > 1:
+        t = torch.tensor([step_ms, verify_ms, kv_ms, e2e["seconds"] if e2e else 0.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms, verify_ms, kv_ms, e2e_s = (float(x) for x in t.tolist())
+        c = torch.tensor([tokens_per_step, float(e2e["tokens"]) if e2e else 0.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        tokens_per_step_all, e2e_tokens_all = (float(x) for x in c.tolist())
+    else:
+        tokens_per_step_all = tokens_per_step
+        e2e_s = e2e["seconds"] if e2e else 0.0
+        e2e_tokens_all = float(e2e["tokens"]) if e2e else 0.0
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        verify_bytes = B * R * V * 2
+        kv_bytes = arena.step_bytes(mean_keep, R, True)
+        v_gbs = verify_bytes / (verify_ms * 1e-3) / 1e9
+        kv_gbs = kv_bytes / (kv_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": tokens_per_step_all / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, world),
+            "tokens_per_step": tokens_per_step_all, "positions_per_s": B * world * R / (step_ms * 1e-3),
+            "mean_accept_len": mean_keep - 1.0,
+            "gpu_launches": args.steps * 2,
+            "launches_per_step": {"sd_verify_kernel": 1, "sd_kv_append_kernel": 1, "nccl_allgather": 1 if world > 1 else 0},
+            "roofline": {"bound": "hbm", "kernel": "verify_kernel<bf16>", "achieved": v_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": v_gbs / peak, "frac_of_8TBs_nominal": v_gbs / 8000.0, "traffic": None,
+                         "algorithmic_bytes": verify_bytes, "us_per_launch": verify_ms * 1e3, "peak_source": peak_src},
+            "roofline_kv": {"bound": "hbm", "kernel": "kv_append_kernel", "achieved": kv_gbs, "peak": peak, "unit": "GB/s",
+                            "frac": kv_gbs / peak, "algorithmic_bytes": kv_bytes, "us_per_launch": kv_ms * 1e3,
+                            "mean_rows_kept": mean_keep},
+            "step_hbm_frac": (verify_bytes + kv_bytes) / (step_ms * 1e-3) / 1e9 / peak,
+            "clocks": clocks, "wall_s_timed_region": t_wall,
+        }
+        if e2e:
+            line["e2e"] = {"value": e2e_tokens_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
+                           "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
+                           "api": "VerifyStep static buffers <- pinned host tensors; packed [B,K+2] record -> host"}
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            tv, tk, reps = cpu_port_step_time(B, K, V, 2, CFG["Hkv"], CFG["D"], CFG["L"], 4, 3, cores)
+            t_cpu = tv + tk * CFG["layers"]
+            line["cpu_baseline"] = {
+                "value": B * (1 + expected_accept(CFG["p_match"], K)) / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": (f"median of {reps} steps on rank 0: torch-CPU port of verify_prefix_ref + argmax bonus on full "
+                           f"[{B},{R},{V}] bf16 logits ({tv * 1e3:.1f} ms) + kv_append_ref torch.cat L={CFG['L']} on 2 of "
+                           f"{CFG['layers']} layers scaled to {CFG['layers']} ({tk * 1e3:.1f} ms/layer)"),
+            }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

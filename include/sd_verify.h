@@ -1,0 +1,215 @@
+/*
+ * sd_verify.h -- C ABI of the B200-native speculative-decoding verify path.
+ *
+ * One shared library (libsd_verify_b200.so, built from llm-inference-lab_b200/csrc for sm_100a)
+ * exports exactly the entry points below.  They are what a foreign-function binding of the
+ * reference (GogoRit/llm-inference-lab) would bind for this path; each entry cites the reference
+ * interface it replaces (paths relative to the reference root).  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Nothing here
+ *     allocates, synchronises or keeps global state: every call only enqueues work on `stream`,
+ *     so calls are CUDA-graph capturable and callers keep ownership of every buffer.
+ *   - Return value: 0 = success; > 0 = a cudaError_t from the launch; < 0 = an sd_status
+ *     argument error (nothing was enqueued).  sd_error_string() names either.
+ *   - Strides are in ELEMENTS for logits / ids and in BYTES for KV tensors (stated per argument).
+ *   - No CPU fallback exists: on a machine without an sm_100 device the launches fail loudly.
+ */
+#ifndef SD_VERIFY_H_
+#define SD_VERIFY_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD_ABI_VERSION 1
+
+/* element type of logits / KV / attention tensors */
+enum sd_dtype { SD_F32 = 0, SD_F16 = 1, SD_BF16 = 2 };
+/* element type of token ids */
+enum sd_id_dtype { SD_I32 = 0, SD_I64 = 1 };
+
+enum sd_status {
+    SD_OK = 0,
+    SD_ERR_INVALID_ARG = -1, /* null pointer, negative size, unknown dtype */
+    SD_ERR_SHAPE = -2,       /* reference raises AssertionError: B / K / H / D mismatch */
+    SD_ERR_WORKSPACE = -3,   /* workspace too small or missing */
+    SD_ERR_ALIGNMENT = -4,   /* pointer / stride not aligned to the element size */
+    SD_ERR_UNSUPPORTED = -5, /* e.g. head_dim not supported by the attention kernel */
+    SD_ERR_CAPACITY = -6     /* KV arena capacity would be exceeded (checked on host-known sizes) */
+};
+
+/* acceptance rule evaluated by sd_verify_step */
+enum sd_accept_mode {
+    SD_ACCEPT_GREEDY = 0,     /* argmax == draft           reference: src/kernels/reference.py:37-54 */
+    SD_ACCEPT_TYPICAL = 1,    /* softmax(target)[draft] >= threshold
+                                 reference: src/specdec/policies/policies.py:358-373 */
+    SD_ACCEPT_CONFIDENCE = 2  /* max softmax(logits) >= threshold
+                                 reference: src/specdec/policies/policies.py:240-250 */
+};
+
+int sd_abi_version(void);
+const char* sd_error_string(int code);
+/* Fills SM count and compute capability of the current device.  Returns 0 or a cudaError_t. */
+int sd_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Kernel 1: fused verify.
+ *
+ * Replaces  verify_prefix(logits[B,K,V], draft_ids[B,K]) -> (accept_len[B] i32, mask[B,K] u8)
+ *           reference: src/kernels/reference.py:13-56 (oracle), src/kernels/triton/verify.py:101-169
+ *           (on-GPU incumbent), src/kernels/cuda/verify.cu:154-217 (never registered);
+ *           call site src/specdec/policies/policies.py:128-134.
+ * and, when rows == K + 1, additionally the per-sequence bonus-token selection of
+ *           src/specdec/core/pipeline.py:3140-3163 / :3174-3206 / :3341-3362 (greedy branch
+ *           :135-137): bonus[b] = argmax(logits[b, accept_len[b], :]).
+ *
+ * logits      [B, rows, V], element strides (stride_b, stride_r, 1); rows == K or K + 1
+ * draft_ids   [B, K], element strides (id_stride_b, 1)
+ * accept_len  [B] int32                 (required)
+ * accepted_mask [B, K] uint8            (nullable)
+ * target_ids  [B, rows] int32           (nullable)  argmax of every row, torch.argmax semantics:
+ *                                        first maximal index, NaN maximal (first NaN), -0 == +0
+ * bonus       [B] int32                 (nullable)  target_ids[b, accept_len[b]] (rows == K+1) else -1
+ * packed      [B, K + 2] int32          (nullable)  {accept_len, target_ids[0..K]} -- the record the
+ *                                        multi-GPU allgather exchanges (target_ids[K] = -1 if rows == K)
+ * workspace   sd_verify_workspace_bytes(B, rows) bytes, zeroed once with sd_verify_workspace_init;
+ *             the kernel leaves it zeroed again, so one init serves any number of launches
+ *             (including graph replays).  Must not be shared by launches that may overlap.
+ *
+ * One kernel launch.  Algorithmic traffic: B * rows * V * sizeof(element) bytes read once.
+ * ------------------------------------------------------------------------------------------ */
+size_t sd_verify_workspace_bytes(int B, int rows);
+int sd_verify_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
+
+int sd_verify_prefix(const void* logits, int logit_dtype, int64_t stride_b, int64_t stride_r,
+                     const void* draft_ids, int id_dtype, int64_t id_stride_b,
+                     int32_t* accept_len, uint8_t* accepted_mask, int32_t* target_ids,
+                     int32_t* bonus, int32_t* packed, void* workspace, size_t workspace_bytes,
+                     int B, int rows, int K, int V, void* stream);
+
+/*
+ * Same pass with softmax statistics ("sampling mode"): one read of the logits yields, per row,
+ * the argmax, the row maximum and sum(exp(x - max)); the acceptance rule `mode` is evaluated on
+ * device.  Replaces the per-sequence softmax policies of src/specdec/policies/policies.py:213-396
+ * (TypicalAcceptancePolicy :358-373, ConfidenceThresholdPolicy :240-250) for a whole batch.
+ *
+ * inv_temperature multiplies the logits before the softmax (1.0f = none;
+ *                 reference: src/specdec/core/pipeline.py:91-92 divides by temperature).
+ * token_prob  [B, K] float (nullable)   softmax(logits[b,k])[draft_ids[b,k]]
+ * row_max     [B, rows] float (nullable) max_v logits * inv_temperature
+ * row_sumexp  [B, rows] float (nullable) sum_v exp(logits * inv_temperature - row_max)
+ *                                        (max probability of the row = 1 / row_sumexp)
+ * Other arguments as sd_verify_prefix.  accept_len is the leading run of positions passing `mode`.
+ */
+int sd_verify_step(const void* logits, int logit_dtype, int64_t stride_b, int64_t stride_r,
+                   const void* draft_ids, int id_dtype, int64_t id_stride_b, int mode,
+                   float threshold, float inv_temperature, int32_t* accept_len,
+                   uint8_t* accepted_mask, int32_t* target_ids, int32_t* bonus, int32_t* packed,
+                   float* token_prob, float* row_max, float* row_sumexp, void* workspace,
+                   size_t workspace_bytes, int B, int rows, int K, int V, void* stream);
+
+/* Tuning hook used by tools/ and bench.py sweeps: threads per CTA (128..1024, multiple of 32),
+ * 16-byte vectors in flight per thread (1..16), 0 restores the built-in heuristic. */
+int sd_verify_set_tuning(int threads, int vectors_per_thread);
+
+/* ------------------------------------------------------------------------------------------
+ * Kernel 2: kv_append into a preallocated arena, with rollback of rejected slots.
+ *
+ * Replaces  kv_append(base_k, base_v, new_k, new_v) -> cat on dim 2
+ *           reference: src/kernels/reference.py:59-93; call site
+ *           src/specdec/models/hf_wrappers.py:985-1030 (one call per layer + device sync)
+ * and       kv_append_with_mask(base_k, base_v, draft_k, draft_v, mask, accept_len, offset)
+ *           reference: src/kernels/reference.py:96-159; src/kernels/cuda/kv_cache.cu:14-95
+ * and the rollback of src/specdec/cache/kv_cache_manager.py:353-479 (realign_kv_cache), which in
+ * the arena layout is a length update plus zeroing of the rejected slots.
+ *
+ * One launch serves every layer.  `layers` is a DEVICE array of n_layers records:
+ */
+typedef struct sd_kv_layer {
+    void* arena_k;      /* [B, H, C, D] rows of row_bytes; byte strides arena_stride_{b,h}, row stride row_bytes */
+    void* arena_v;
+    const void* new_k;  /* [B, H, R, D] offered rows; byte strides new_stride_{b,h,r} */
+    const void* new_v;
+} sd_kv_layer;
+
+/*
+ * For every layer, K and V, sequence b and head h:
+ *   n   = n_keep ? clamp(n_keep[b] + keep_bias, 0, R) : R
+ *   dst = arena[b, h, seq_lens[b] + j]   for j in [0, R)
+ *   accepted_mask == NULL : dst_j = new[b, h, j]          for j <  n
+ *   accepted_mask != NULL : dst_j = new[b, h, idx_j(b)]   for j <  n, idx_j = position of the j-th set
+ *                           bit of accepted_mask[b, 0..R)  (reference.py:149-157 compaction)
+ *   zero_rejected         : dst_j = 0                     for n <= j < R      (reference.py:133-134)
+ * and, after every copy has been issued, seq_lens_out[b] = seq_lens[b] + n (seq_lens_out may alias
+ * seq_lens: the update is performed by the last CTA to retire).  n_keep is typically the
+ * accept_len written by sd_verify_prefix on the same stream with keep_bias = 1 (accepted drafts +
+ * the token they were conditioned on), so no host round trip separates verify from append.
+ *
+ * seq_lens    [B] int32  rows already valid per sequence (NULL = all zero)
+ * capacity    C; the host-checkable bound max_seq_len_host + R <= C is verified when
+ *             max_seq_len_host >= 0; on device, rows that would fall beyond C are dropped and
+ *             *overflow_flag (nullable, int32) is set non-zero.
+ * ticket      one int32 in device memory, zero before the first launch (the kernel re-zeroes it).
+ *
+ * Algorithmic traffic per launch: n_layers * 2 * B * H * row_bytes * (mean n read + R written
+ * when zero_rejected, else mean n written).
+ */
+int sd_kv_append(const sd_kv_layer* layers, int n_layers, int B, int H, int R, int64_t row_bytes,
+                 int64_t capacity, int64_t arena_stride_b, int64_t arena_stride_h,
+                 int64_t new_stride_b, int64_t new_stride_h, int64_t new_stride_r,
+                 const int32_t* seq_lens, int32_t* seq_lens_out, const int32_t* n_keep,
+                 int keep_bias, const uint8_t* accepted_mask, int zero_rejected,
+                 int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, void* stream);
+
+/*
+ * Single-layer form with the layer record passed by value and a uniform current length
+ * `base_len` (every sequence holds base_len rows): the building block of the functional drop-ins
+ *   kv_append(base_k, base_v, new_k, new_v)                       reference.py:59-93
+ *   kv_append_with_mask(base_k, ..., accepted_mask, accept_len)   reference.py:96-159
+ * whose outputs are views [B,H,base_len+R,D] of the arena.  Same per-row semantics as sd_kv_append.
+ */
+int sd_kv_append_layer(void* arena_k, void* arena_v, const void* new_k, const void* new_v, int B, int H,
+                       int R, int64_t row_bytes, int64_t capacity, int64_t arena_stride_b,
+                       int64_t arena_stride_h, int64_t new_stride_b, int64_t new_stride_h,
+                       int64_t new_stride_r, int64_t base_len, const int32_t* n_keep, int keep_bias,
+                       const uint8_t* accepted_mask, int zero_rejected, int32_t* ticket, void* stream);
+
+/* Variant selector for sd_kv_append (evidence runs): 0 = heuristic, 1 = 128-bit LDG/STG kernel,
+ * 2 = cp.async.bulk (TMA 1-D) shared-memory staged kernel. */
+int sd_kv_set_variant(int variant);
+
+/* ------------------------------------------------------------------------------------------
+ * Kernel 3: (K+1)-query causal decode attention for the verify pass (GQA aware, split-KV).
+ *
+ * Replaces the target model's attention inner loop during verification, which the reference runs as
+ * K sequential single-query SDPA calls inside `transformers`
+ * (src/specdec/models/hf_wrappers.py:98 attn_implementation="sdpa";
+ *  src/scheduler/speculative_scheduler.py:192-199 K greedy steps), with ONE pass over the KV cache.
+ *
+ * q        [B, Hq, R, D]   contiguous, dtype f16/bf16; R = K+1 <= 8 new positions
+ * k_arena  [B, Hkv, C, D]  byte strides kv_stride_b, kv_stride_h, row stride D*elt; the R new rows
+ *                          are already appended: rows [0, seq_lens[b] + R) are valid
+ * v_arena  same layout
+ * seq_lens [B] int32       rows valid BEFORE the R new ones (query i sees rows [0, seq_lens[b]+i])
+ * out      [B, Hq, R, D]   same dtype as q
+ * workspace sd_verify_attention_workspace_bytes(...) bytes (split-KV partials), no init needed
+ * scale    softmax scale (1/sqrt(D) when <= 0)
+ * n_splits 0 = heuristic
+ * Algorithmic traffic: 2 * B * Hkv * (mean len + R) * D * elt bytes of KV read once per launch.
+ */
+size_t sd_verify_attention_workspace_bytes(int B, int Hq, int R, int D, int max_splits);
+int sd_verify_attention(const void* q, const void* k_arena, const void* v_arena,
+                        const int32_t* seq_lens, void* out, void* workspace,
+                        size_t workspace_bytes, int dtype, int B, int Hq, int Hkv, int R, int D,
+                        int64_t kv_stride_b, int64_t kv_stride_h, int64_t max_seq_len_host,
+                        float scale, int n_splits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SD_VERIFY_H_ */

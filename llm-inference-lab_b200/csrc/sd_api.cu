@@ -1,0 +1,46 @@
+// Library-level entry points: ABI version, error strings, device query.
+#include "sd_common.cuh"
+
+extern "C" {
+
+int sd_abi_version(void) { return SD_ABI_VERSION; }
+
+const char* sd_error_string(int code) {
+    switch (code) {
+        case SD_OK: return "ok";
+        case SD_ERR_INVALID_ARG: return "invalid argument";
+        case SD_ERR_SHAPE: return "shape mismatch";
+        case SD_ERR_WORKSPACE: return "workspace missing or too small";
+        case SD_ERR_ALIGNMENT: return "pointer or stride misaligned";
+        case SD_ERR_UNSUPPORTED: return "unsupported configuration";
+        case SD_ERR_CAPACITY: return "KV arena capacity exceeded";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+    return "unknown sd_status";
+}
+
+int sd_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    int v = 0;
+    if (sm_count) {
+        e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return (int)e;
+        *sm_count = v;
+    }
+    if (cc_major) {
+        e = cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev);
+        if (e != cudaSuccess) return (int)e;
+        *cc_major = v;
+    }
+    if (cc_minor) {
+        e = cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev);
+        if (e != cudaSuccess) return (int)e;
+        *cc_minor = v;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+// Shared device helpers for the sm_100a verify-path kernels.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sd_verify.h"
+
+#define SD_DEVINL __device__ __forceinline__
+
+namespace sd {
+
+constexpr int kWarp = 32;
+
+// ---- streaming global loads: read-once data must not displace the KV working set in L1 ----
+SD_DEVINL uint4 ldg_stream_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+SD_DEVINL void stg_stream_v4(void* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// ---- order-preserving key for a float under torch.argmax semantics ----
+// larger key == "more maximal": NaN > +inf > ... > +0 == -0 > ... > -inf.
+SD_DEVINL uint32_t order_key(float f) {
+    uint32_t u = __float_as_uint(f);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu;  // NaN: maximal, all NaNs equal
+    if (u == 0x80000000u) u = 0u;                             // -0 == +0
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// inverse of order_key for non-NaN keys (NaN key -> quiet NaN)
+SD_DEVINL float key_to_float(uint32_t k) {
+    if (k == 0xffffffffu) return __uint_as_float(0x7fc00000u);
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+template <typename T>
+SD_DEVINL float to_float(T v);
+template <>
+SD_DEVINL float to_float<float>(float v) { return v; }
+template <>
+SD_DEVINL float to_float<__half>(__half v) { return __half2float(v); }
+template <>
+SD_DEVINL float to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// ---- packed max with NaN propagation (canonical NaN result), per 32-bit word ----
+template <typename T>
+struct Packed;  // operations on one 32-bit word holding 1 (fp32) or 2 (16-bit) elements
+
+template <>
+struct Packed<float> {
+    static constexpr int kPerWord = 1;
+    static constexpr uint32_t kNegInf = 0xff800000u;
+    SD_DEVINL static uint32_t vmax(uint32_t a, uint32_t b) {
+        uint32_t d;
+        asm("max.NaN.f32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+        return d;
+    }
+    // fold the word to a scalar replicated in every lane of the word, with -0 -> +0
+    SD_DEVINL static uint32_t fold(uint32_t w) {
+        uint32_t d;
+        asm("add.rn.f32 %0, %1, 0f00000000;" : "=r"(d) : "r"(w));
+        return d;
+    }
+    SD_DEVINL static float scalar(uint32_t w) { return __uint_as_float(w); }
+};
+
+template <>
+struct Packed<__half> {
+    static constexpr int kPerWord = 2;
+    static constexpr uint32_t kNegInf = 0xfc00fc00u;
+    SD_DEVINL static uint32_t vmax(uint32_t a, uint32_t b) {
+        uint32_t d;
+        asm("max.NaN.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+        return d;
+    }
+    SD_DEVINL static uint32_t fold(uint32_t w) {
+        uint32_t sw = __byte_perm(w, w, 0x1032);
+        uint32_t m = vmax(w, sw), d, z = 0u;
+        asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(m), "r"(z));
+        return d;
+    }
+    SD_DEVINL static float scalar(uint32_t w) {
+        return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu)));
+    }
+};
+
+template <>
+struct Packed<__nv_bfloat16> {
+    static constexpr int kPerWord = 2;
+    static constexpr uint32_t kNegInf = 0xff80ff80u;
+    SD_DEVINL static uint32_t vmax(uint32_t a, uint32_t b) {
+        uint32_t d;
+        asm("max.NaN.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+        return d;
+    }
+    SD_DEVINL static uint32_t fold(uint32_t w) {
+        uint32_t sw = __byte_perm(w, w, 0x1032);
+        uint32_t m = vmax(w, sw), d, z = 0u;
+        asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(m), "r"(z));
+        return d;
+    }
+    SD_DEVINL static float scalar(uint32_t w) { return __uint_as_float(w << 16); }
+};
+
+// 2^x, MUFU.EX2 (approx, flush-to-zero): relative error ~2^-22, exact for x == 0
+SD_DEVINL float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+SD_DEVINL int load_id(const void* ids, int id_dtype, int64_t i) {
+    // ids outside int32 can never equal an argmax index; clamp them to -1 so equality fails
+    if (id_dtype == SD_I32) return reinterpret_cast<const int32_t*>(ids)[i];
+    long long v = reinterpret_cast<const long long*>(ids)[i];
+    return (v < 0 || v > 0x7fffffffLL) ? -1 : (int)v;
+}
+
+inline int elt_size(int dtype) { return dtype == SD_F32 ? 4 : 2; }
+
+inline int to_status(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
+
+}  // namespace sd

@@ -1,0 +1,99 @@
+"""ctypes binding of include/sd_verify.h (the C ABI of libsd_verify_b200.so).
+
+This is the "thin C-ABI extension": plain pointers and sizes, no torch types.  ``cuda_ops.py``
+wraps these calls as torch custom ops; ``INTEGRATION.md`` shows the same binding written for the
+reference tree.  Importing this module never falls back to another implementation: a missing or
+stale library is rebuilt with nvcc, and failure raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import re
+from pathlib import Path
+from typing import List
+
+from . import build as _build
+
+DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
+ID_I32, ID_I64 = 0, 1
+ACCEPT_GREEDY, ACCEPT_TYPICAL, ACCEPT_CONFIDENCE = 0, 1, 2
+ABI_VERSION = 1
+
+_vp = C.c_void_p
+_i = C.c_int
+_i64 = C.c_int64
+_f = C.c_float
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); must list every function include/sd_verify.h declares
+SIGNATURES = {
+    "sd_abi_version": (_i, []),
+    "sd_error_string": (C.c_char_p, [_i]),
+    "sd_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "sd_verify_workspace_bytes": (_sz, [_i, _i]),
+    "sd_verify_workspace_init": (_i, [_vp, _sz, _vp]),
+    "sd_verify_prefix": (_i, [_vp, _i, _i64, _i64, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                              _i, _i, _i, _i, _vp]),
+    "sd_verify_step": (_i, [_vp, _i, _i64, _i64, _vp, _i, _i64, _i, _f, _f, _vp, _vp, _vp, _vp, _vp,
+                            _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp]),
+    "sd_verify_set_tuning": (_i, [_i, _i]),
+    "sd_kv_append": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp,
+                          _i, _vp, _i, _i64, _vp, _vp, _vp]),
+    "sd_kv_append_layer": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
+                                _vp, _i, _vp, _i, _vp, _vp]),
+    "sd_kv_set_variant": (_i, [_i]),
+    "sd_verify_attention_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "sd_verify_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i64, _i64,
+                                 _i64, _f, _i, _vp]),
+}
+
+
+def declared_symbols(header: Path | None = None) -> List[str]:
+    """Function names declared in include/sd_verify.h (used by the symbol-export test)."""
+    header = header or (_build.INCLUDE / "sd_verify.h")
+    text = re.sub(r"/\*.*?\*/", "", header.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(sd_[a-z0-9_]+)\s*\(", text)))
+
+
+class SdError(RuntimeError):
+    def __init__(self, code: int, what: str):
+        super().__init__(f"{what}: {code} ({_error_string(code)})")
+        self.code = code
+
+
+class Lib:
+    """Loaded library with typed entry points."""
+
+    def __init__(self, path: Path):
+        self.path = Path(path)
+        self.cdll = C.CDLL(str(path))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(self.cdll, name)  # AttributeError here == symbol not exported: loud
+            fn.restype = res
+            fn.argtypes = args
+            setattr(self, name, fn)
+        got = self.sd_abi_version()
+        if got != ABI_VERSION:
+            raise RuntimeError(f"{path}: ABI version {got}, binding expects {ABI_VERSION}")
+
+    def check(self, code: int, what: str) -> None:
+        if code != 0:
+            raise SdError(code, what)
+
+
+_LIB: Lib | None = None
+
+
+def lib() -> Lib:
+    global _LIB
+    if _LIB is None:
+        _LIB = Lib(_build.build_cuda_kernels())
+    return _LIB
+
+
+def _error_string(code: int) -> str:
+    try:
+        return lib().sd_error_string(code).decode()
+    except Exception:  # pragma: no cover
+        return "?"

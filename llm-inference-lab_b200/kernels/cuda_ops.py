@@ -1,0 +1,504 @@
+"""Host side of the B200 verify path: torch tensors in, C-ABI launches out.
+
+Everything here is plumbing around ``libsd_verify_b200.so`` (include/sd_verify.h): argument
+checking with the reference's error behaviour, output allocation with the torch allocator, and
+launching on torch's CURRENT stream (the reference's own .cu files launched on the legacy default
+stream -- src/kernels/cuda/verify.cu:196 -- which breaks ``torch.cuda.stream`` callers).  No function
+in this module synchronises the device or falls back to a CPU / PyTorch implementation: inputs that
+are not CUDA tensors raise.
+
+The functions registered in the kernel registry are the ``*_cuda`` ones; their ``__name__`` contains
+"cuda" because ``get_kernel_info`` classifies backends by name
+(reference: src/kernels/__init__.py:129-147).  The same entry points are also exposed as torch custom
+ops under the ``sd_b200::`` namespace (see ``_register_torch_ops``).
+"""
+
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _capi
+
+_DTYPE = {torch.float32: _capi.DTYPE_F32, torch.float16: _capi.DTYPE_F16, torch.bfloat16: _capi.DTYPE_BF16}
+_ID_DTYPE = {torch.int32: _capi.ID_I32, torch.int64: _capi.ID_I64}
+
+ACCEPT_MODES = {"greedy": _capi.ACCEPT_GREEDY, "typical": _capi.ACCEPT_TYPICAL, "confidence": _capi.ACCEPT_CONFIDENCE}
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what} must be a CUDA tensor: the sd_b200 kernels have no CPU implementation "
+            f"(got device {t.device})"
+        )
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _Scratch:
+    """Per (device, stream) scratch: verify workspaces and kv tickets.
+
+    A workspace must not be shared by launches that can overlap, so the cache key includes the
+    stream.  While a CUDA graph is being captured nothing is cached: the allocation belongs to the
+    graph's private pool and stays alive with the graph."""
+
+    def __init__(self) -> None:
+        self._ws: Dict[Tuple[int, int, int], torch.Tensor] = {}
+        self._ticket: Dict[Tuple[int, int], torch.Tensor] = {}
+
+    def workspace(self, device: torch.device, B: int, rows: int) -> torch.Tensor:
+        need = int(_capi.lib().sd_verify_workspace_bytes(B, rows))
+        if torch.cuda.is_current_stream_capturing():
+            return torch.zeros(need, dtype=torch.uint8, device=device)
+        key = (device.index or 0, _stream_ptr(device), 0)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
+            self._ws[key] = ws
+        return ws
+
+    def ticket(self, device: torch.device) -> torch.Tensor:
+        if torch.cuda.is_current_stream_capturing():
+            return torch.zeros(1, dtype=torch.int32, device=device)
+        key = (device.index or 0, _stream_ptr(device))
+        t = self._ticket.get(key)
+        if t is None:
+            t = torch.zeros(1, dtype=torch.int32, device=device)
+            self._ticket[key] = t
+        return t
+
+
+_scratch = _Scratch()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------ verify
+def _check_verify_inputs(logits: torch.Tensor, draft_ids: torch.Tensor, rows_extra: int):
+    # same assertions as the reference (src/kernels/reference.py:27-31) -> AssertionError
+    assert logits.dim() == 3, "logits must be 3D tensor [B][K][V]"
+    assert draft_ids.dim() == 2, "draft_ids must be 2D tensor [B][K]"
+    assert logits.size(0) == draft_ids.size(0), "Batch size mismatch"
+    assert logits.size(1) == draft_ids.size(1) + rows_extra, "K dimension mismatch"
+    _require_cuda(logits, "logits")
+    if logits.dtype not in _DTYPE:
+        raise TypeError(f"logits dtype {logits.dtype} not supported (float32 / float16 / bfloat16)")
+    if draft_ids.device != logits.device:
+        draft_ids = draft_ids.to(logits.device)
+    if draft_ids.dtype not in _ID_DTYPE:
+        draft_ids = draft_ids.to(torch.int64)
+    if logits.size(2) > 0 and logits.stride(2) != 1:
+        logits = logits.contiguous()
+    if draft_ids.size(1) > 0 and draft_ids.stride(1) != 1:
+        draft_ids = draft_ids.contiguous()
+    return logits, draft_ids
+
+
+def verify_launch(
+    logits: torch.Tensor,
+    draft_ids: torch.Tensor,
+    accept_len: torch.Tensor,
+    accepted_mask: Optional[torch.Tensor] = None,
+    target_ids: Optional[torch.Tensor] = None,
+    bonus: Optional[torch.Tensor] = None,
+    packed: Optional[torch.Tensor] = None,
+    workspace: Optional[torch.Tensor] = None,
+    *,
+    mode: int = _capi.ACCEPT_GREEDY,
+    threshold: float = 0.0,
+    inv_temperature: float = 1.0,
+    token_prob: Optional[torch.Tensor] = None,
+    row_max: Optional[torch.Tensor] = None,
+    row_sumexp: Optional[torch.Tensor] = None,
+    stats: bool = False,
+) -> None:
+    """Enqueue one fused-verify launch into caller-owned buffers (no allocation when a workspace is
+    passed).  This is the call the graph-captured step uses."""
+    B, rows, V = logits.shape
+    K = draft_ids.shape[1]
+    dev = logits.device
+    if workspace is None:
+        workspace = _scratch.workspace(dev, B, rows)
+    lib = _capi.lib()
+    common = (
+        logits.data_ptr(), _DTYPE[logits.dtype], logits.stride(0), logits.stride(1),
+        draft_ids.data_ptr(), _ID_DTYPE[draft_ids.dtype], draft_ids.stride(0),
+    )
+    with torch.cuda.device(dev):
+        if stats or mode != _capi.ACCEPT_GREEDY:
+            rc = lib.sd_verify_step(
+                *common, mode, float(threshold), float(inv_temperature),
+                accept_len.data_ptr(), _ptr(accepted_mask), _ptr(target_ids), _ptr(bonus), _ptr(packed),
+                _ptr(token_prob), _ptr(row_max), _ptr(row_sumexp),
+                workspace.data_ptr(), workspace.numel(), B, rows, K, V, _stream_ptr(dev),
+            )
+        else:
+            rc = lib.sd_verify_prefix(
+                *common, accept_len.data_ptr(), _ptr(accepted_mask), _ptr(target_ids), _ptr(bonus), _ptr(packed),
+                workspace.data_ptr(), workspace.numel(), B, rows, K, V, _stream_ptr(dev),
+            )
+    lib.check(rc, "sd_verify")
+
+
+def verify_prefix_cuda(logits: torch.Tensor, draft_ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Drop-in for the registry op ``verify_prefix``.
+
+    reference: src/kernels/reference.py:13-56 (semantics), src/kernels/triton/verify.py:101-169
+    (the incumbent it outranks), call site src/specdec/policies/policies.py:128-134.
+    logits [B,K,V] fp32/fp16/bf16 (batch slices welcome), draft_ids [B,K] int -> (accept_len [B]
+    int32, accepted_mask [B,K] uint8) on logits.device, enqueued on the current stream, no sync."""
+    logits, draft_ids = _check_verify_inputs(logits, draft_ids, 0)
+    B, K, _ = logits.shape
+    accept_len = torch.empty(B, dtype=torch.int32, device=logits.device)
+    mask = torch.empty((B, K), dtype=torch.uint8, device=logits.device)
+    if B == 0:
+        return accept_len, mask
+    if K == 0:
+        return accept_len.zero_(), mask
+    if logits.size(2) == 0:
+        raise RuntimeError("verify_prefix: empty vocabulary")
+    verify_launch(logits, draft_ids, accept_len, mask)
+    return accept_len, mask
+
+
+def verify_prefix_bonus_cuda(logits: torch.Tensor, draft_ids: torch.Tensor):
+    """Fused verify over K+1 target rows (new registry op ``verify_prefix_bonus``).
+
+    logits [B,K+1,V], draft_ids [B,K] -> (accept_len [B] i32, accepted_mask [B,K] u8,
+    target_ids [B,K+1] i32, bonus [B] i32, packed [B,K+2] i32).  bonus[b] is the greedy token of row
+    accept_len[b] (reference: src/specdec/core/pipeline.py:3140-3163, :3174-3206, :3341-3362)."""
+    logits, draft_ids = _check_verify_inputs(logits, draft_ids, 1)
+    B, rows, _ = logits.shape
+    K = rows - 1
+    dev = logits.device
+    accept_len = torch.empty(B, dtype=torch.int32, device=dev)
+    mask = torch.empty((B, K), dtype=torch.uint8, device=dev)
+    target_ids = torch.empty((B, rows), dtype=torch.int32, device=dev)
+    bonus = torch.empty(B, dtype=torch.int32, device=dev)
+    packed = torch.empty((B, K + 2), dtype=torch.int32, device=dev)
+    if B > 0:
+        if logits.size(2) == 0:
+            raise RuntimeError("verify_prefix_bonus: empty vocabulary")
+        verify_launch(logits, draft_ids, accept_len, mask, target_ids, bonus, packed)
+    return accept_len, mask, target_ids, bonus, packed
+
+
+def verify_step_cuda(
+    logits: torch.Tensor,
+    draft_ids: torch.Tensor,
+    mode: str = "typical",
+    threshold: float = 0.9,
+    temperature: float = 1.0,
+):
+    """Sampling-mode verify (new registry op ``verify_step``): the same single pass also yields the
+    softmax statistics and evaluates the acceptance rule on device.
+
+    mode "typical":    accept while softmax(target)[draft] >= threshold (policies.py:358-373)
+    mode "confidence": accept while max softmax(logits) >= threshold     (policies.py:240-250)
+    mode "greedy":     argmax match, statistics still returned
+    logits [B,K or K+1,V].  Returns dict(accept_len, accepted_mask, target_ids, bonus, token_prob,
+    row_max, row_sumexp)."""
+    rows_extra = logits.size(1) - draft_ids.size(1)
+    assert rows_extra in (0, 1), "logits must carry K or K+1 rows"
+    logits, draft_ids = _check_verify_inputs(logits, draft_ids, rows_extra)
+    if temperature <= 0:
+        raise ValueError("temperature must be > 0")
+    B, rows, _ = logits.shape
+    K = draft_ids.shape[1]
+    dev = logits.device
+    out = {
+        "accept_len": torch.empty(B, dtype=torch.int32, device=dev),
+        "accepted_mask": torch.empty((B, K), dtype=torch.uint8, device=dev),
+        "target_ids": torch.empty((B, rows), dtype=torch.int32, device=dev),
+        "bonus": torch.empty(B, dtype=torch.int32, device=dev),
+        "token_prob": torch.empty((B, K), dtype=torch.float32, device=dev),
+        "row_max": torch.empty((B, rows), dtype=torch.float32, device=dev),
+        "row_sumexp": torch.empty((B, rows), dtype=torch.float32, device=dev),
+    }
+    if B > 0:
+        verify_launch(
+            logits, draft_ids, out["accept_len"], out["accepted_mask"], out["target_ids"], out["bonus"], None,
+            mode=ACCEPT_MODES[mode], threshold=threshold, inv_temperature=1.0 / temperature,
+            token_prob=out["token_prob"], row_max=out["row_max"], row_sumexp=out["row_sumexp"], stats=True,
+        )
+    return out
+
+
+# ------------------------------------------------------------------------------------------ kv append
+class _ArenaTag:
+    """Attached (attribute ``_sd_arena``) to the [B,H,C,D] buffer behind tensors returned by
+    ``kv_append_cuda``: how many rows are valid and which buffer is its K/V partner."""
+
+    __slots__ = ("used", "capacity")
+
+    def __init__(self, used: int, capacity: int) -> None:
+        self.used = used
+        self.capacity = capacity
+
+
+def _arena_of(t: torch.Tensor, L: int):
+    """If ``t`` is the [:, :, :L] prefix view of one of our arenas, return (arena, tag)."""
+    base = t._base
+    if base is None:
+        return None
+    tag = getattr(base, "_sd_arena", None)
+    if tag is None or base.dim() != 4 or t.data_ptr() != base.data_ptr():
+        return None
+    if t.shape[0] != base.shape[0] or t.shape[1] != base.shape[1] or t.shape[3] != base.shape[3]:
+        return None
+    if t.stride() != base.stride() and t.numel() > 0:
+        return None
+    if L > tag.used:
+        return None
+    return base, tag
+
+
+def _grow_capacity(need: int) -> int:
+    # geometric growth: amortised O(1) bytes copied per appended row (torch.cat costs O(L) each call)
+    return max(64, 1 << (max(need, 1) * 2 - 1).bit_length())
+
+
+def _kv_layer_launch(arena_k, arena_v, new_k, new_v, base_len, n_keep, keep_bias, mask, zero_rejected) -> None:
+    B, H, C, D = arena_k.shape
+    R = new_k.shape[2]
+    es = arena_k.element_size()
+    dev = arena_k.device
+    lib = _capi.lib()
+    with torch.cuda.device(dev):
+        rc = lib.sd_kv_append_layer(
+            arena_k.data_ptr(), arena_v.data_ptr(), new_k.data_ptr(), new_v.data_ptr(), B, H, R, D * es, C,
+            arena_k.stride(0) * es, arena_k.stride(1) * es,
+            new_k.stride(0) * es, new_k.stride(1) * es, new_k.stride(2) * es,
+            base_len, _ptr(n_keep), keep_bias, _ptr(mask), int(zero_rejected),
+            _scratch.ticket(dev).data_ptr(), _stream_ptr(dev),
+        )
+    lib.check(rc, "sd_kv_append_layer")
+
+
+def _same_layout(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return a.shape == b.shape and a.stride() == b.stride()
+
+
+def _rows_operand(t: torch.Tensor) -> torch.Tensor:
+    """Offered rows must have a contiguous head dim; other strides are passed through."""
+    if t.size(3) > 0 and t.stride(3) != 1:
+        t = t.contiguous()
+    return t
+
+
+def _check_kv_inputs(base_k, base_v, new_k, new_v) -> None:
+    # reference assertions: src/kernels/reference.py:77-87
+    assert base_k.dim() == 4, "base_k must be 4D tensor [B][H][L][D]"
+    assert base_v.dim() == 4, "base_v must be 4D tensor [B][H][L][D]"
+    assert new_k.dim() == 4, "new_k must be 4D tensor [B][H][K][D]"
+    assert new_v.dim() == 4, "new_v must be 4D tensor [B][H][K][D]"
+    assert base_k.shape[0] == new_k.shape[0], "Batch size mismatch"
+    assert base_k.shape[1] == new_k.shape[1], "Num heads mismatch"
+    assert base_k.shape[3] == new_k.shape[3], "Head dim mismatch"
+    assert base_k.shape == base_v.shape and new_k.shape == new_v.shape, "K/V shape mismatch"
+    for t, n in ((base_k, "base_k"), (base_v, "base_v"), (new_k, "new_k"), (new_v, "new_v")):
+        _require_cuda(t, n)
+    assert base_k.dtype == base_v.dtype == new_k.dtype == new_v.dtype, "dtype mismatch"
+
+
+def _append_functional(base_k, base_v, new_k, new_v, n_keep, mask, zero_rejected):
+    _check_kv_inputs(base_k, base_v, new_k, new_v)
+    B, H, L, D = base_k.shape
+    R = new_k.shape[2]
+    new_k, new_v = _rows_operand(new_k), _rows_operand(new_v)
+    if not _same_layout(new_k, new_v):
+        new_k, new_v = new_k.contiguous(), new_v.contiguous()
+    hit_k, hit_v = _arena_of(base_k, L), _arena_of(base_v, L)
+    arena_k = arena_v = None
+    if hit_k and hit_v and hit_k[1].capacity == hit_v[1].capacity and L + R <= hit_k[1].capacity:
+        arena_k, tag_k = hit_k
+        arena_v, tag_v = hit_v
+    if arena_k is None:
+        cap = _grow_capacity(L + R)
+        arena_k = torch.empty((B, H, cap, D), dtype=base_k.dtype, device=base_k.device)
+        arena_v = torch.empty((B, H, cap, D), dtype=base_k.dtype, device=base_k.device)
+        tag_k, tag_v = _ArenaTag(0, cap), _ArenaTag(0, cap)
+        arena_k._sd_arena, arena_v._sd_arena = tag_k, tag_v
+        if L > 0 and B * H * D > 0:  # one-time adoption copy of the existing rows (our kernel, R = L)
+            bk, bv = _rows_operand(base_k), _rows_operand(base_v)
+            if not _same_layout(bk, bv):
+                bk, bv = bk.contiguous(), bv.contiguous()
+            _kv_layer_launch(arena_k, arena_v, bk, bv, 0, None, 0, None, False)
+    if R > 0 and B * H * D > 0:
+        _kv_layer_launch(arena_k, arena_v, new_k, new_v, L, n_keep, 0, mask, zero_rejected)
+    tag_k.used = tag_v.used = L + R
+    return arena_k[:, :, : L + R], arena_v[:, :, : L + R]
+
+
+def kv_append_cuda(base_k, base_v, new_k, new_v):
+    """Drop-in for the registry op ``kv_append`` (reference: src/kernels/reference.py:59-93; call site
+    src/specdec/models/hf_wrappers.py:1009).
+
+    Returns (out_k, out_v) = rows of base followed by rows of new, [B,H,L+Kn,D].  The results are
+    views of a geometrically grown arena: when ``base_*`` is itself a result of this function (the
+    reference's usage: ``cache = kv_append(cache, chunk)``), only the Kn new rows move -- O(Kn) bytes
+    instead of torch.cat's O(L).  Aliasing contract: the returned tensors share storage with
+    ``base_*`` in that case; a caller that appends two different chunks to the SAME base must clone
+    the first result (the reference's callers replace their handle, hf_wrappers.py:941-943)."""
+    return _append_functional(base_k, base_v, new_k, new_v, None, None, False)
+
+
+def kv_append_with_mask_cuda(base_k, base_v, draft_k, draft_v, accepted_mask, accept_len, offset: int = 0):
+    """Registry op ``kv_append_with_mask`` (reference: src/kernels/reference.py:96-159): masked rows
+    compacted after the base rows, at most accept_len[b] of them, zero tail; ``offset`` ignored as in
+    the reference.  Zero acceptance keeps the base rows (the reference's dead CUDA kernel zeroed
+    them: src/kernels/cuda/kv_cache.cu:39-40)."""
+    assert accepted_mask.dim() == 2, "accepted_mask must be 2D tensor [B][K]"
+    assert accept_len.dim() == 1, "accept_len must be 1D tensor [B]"
+    dev = base_k.device
+    mask = accepted_mask.to(device=dev, dtype=torch.uint8).contiguous()
+    alen = accept_len.to(device=dev, dtype=torch.int32).contiguous()
+    return _append_functional(base_k, base_v, draft_k, draft_v, alen, mask, True)
+
+
+def kv_arena_append_launch(
+    layer_table: torch.Tensor,
+    n_layers: int,
+    B: int,
+    H: int,
+    R: int,
+    row_bytes: int,
+    capacity: int,
+    arena_strides: Tuple[int, int],
+    new_strides: Tuple[int, int, int],
+    seq_lens: torch.Tensor,
+    seq_lens_out: Optional[torch.Tensor],
+    n_keep: Optional[torch.Tensor],
+    keep_bias: int,
+    accepted_mask: Optional[torch.Tensor],
+    zero_rejected: bool,
+    max_seq_len_host: int,
+    overflow_flag: Optional[torch.Tensor],
+    ticket: torch.Tensor,
+) -> None:
+    """All-layer arena append (sd_kv_append).  ``layer_table`` is a device int64 [n_layers, 4] tensor
+    of (arena_k, arena_v, new_k, new_v) pointers == sd_kv_layer[n_layers]."""
+    dev = layer_table.device
+    lib = _capi.lib()
+    with torch.cuda.device(dev):
+        rc = lib.sd_kv_append(
+            layer_table.data_ptr(), n_layers, B, H, R, row_bytes, capacity, arena_strides[0], arena_strides[1],
+            new_strides[0], new_strides[1], new_strides[2], _ptr(seq_lens), _ptr(seq_lens_out), _ptr(n_keep),
+            keep_bias, _ptr(accepted_mask), int(zero_rejected), max_seq_len_host, _ptr(overflow_flag),
+            ticket.data_ptr(), _stream_ptr(dev),
+        )
+    lib.check(rc, "sd_kv_append")
+
+
+# ------------------------------------------------------------------------------------------ attention
+def verify_attention_cuda(
+    q: torch.Tensor,
+    k_arena: torch.Tensor,
+    v_arena: torch.Tensor,
+    seq_lens: torch.Tensor,
+    scale: Optional[float] = None,
+    max_seq_len: int = -1,
+    n_splits: int = 0,
+    out: Optional[torch.Tensor] = None,
+    workspace: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """(K+1)-query causal decode attention over the KV arena (new registry op ``verify_attention``).
+
+    q [B,Hq,R,D]; k_arena/v_arena [B,Hkv,C,D] with the R new rows already appended at
+    seq_lens[b]..; seq_lens [B] int32 = rows valid before them.  Replaces K sequential SDPA decode
+    steps of the reference (src/scheduler/speculative_scheduler.py:192-199,
+    src/specdec/models/hf_wrappers.py:98)."""
+    assert q.dim() == 4 and k_arena.dim() == 4 and v_arena.dim() == 4
+    _require_cuda(q, "q")
+    B, Hq, R, D = q.shape
+    Hkv, C = k_arena.shape[1], k_arena.shape[2]
+    assert k_arena.shape == v_arena.shape and k_arena.shape[0] == B and k_arena.shape[3] == D
+    assert Hq % Hkv == 0, "query heads must be a multiple of KV heads"
+    assert q.dtype in (torch.float16, torch.bfloat16) and k_arena.dtype == q.dtype == v_arena.dtype
+    assert k_arena.stride(3) == 1 and k_arena.stride(2) == D and k_arena.stride() == v_arena.stride()
+    q = q.contiguous()
+    seq_lens = seq_lens.to(device=q.device, dtype=torch.int32)
+    if out is None:
+        out = torch.empty_like(q)
+    lib = _capi.lib()
+    es = q.element_size()
+    if workspace is None:
+        need = int(lib.sd_verify_attention_workspace_bytes(B, Hq, R, D, 0))
+        workspace = torch.empty(need, dtype=torch.uint8, device=q.device)
+    with torch.cuda.device(q.device):
+        rc = lib.sd_verify_attention(
+            q.data_ptr(), k_arena.data_ptr(), v_arena.data_ptr(), seq_lens.data_ptr(), out.data_ptr(),
+            workspace.data_ptr(), workspace.numel(), _DTYPE[q.dtype], B, Hq, Hkv, R, D,
+            k_arena.stride(0) * es, k_arena.stride(1) * es, max_seq_len,
+            float(scale) if scale is not None else 0.0, n_splits, _stream_ptr(q.device),
+        )
+    lib.check(rc, "sd_verify_attention")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ torch ops
+_TORCH_LIB = None
+
+
+def _register_torch_ops() -> None:
+    """Expose the entry points as torch custom ops (CUDA dispatch key only -> CPU tensors raise
+    NotImplementedError from the dispatcher: there is no CPU kernel to fall back to)."""
+    global _TORCH_LIB
+    if _TORCH_LIB is not None:
+        return
+    lib = torch.library.Library("sd_b200", "DEF")
+    lib.define("verify_prefix(Tensor logits, Tensor draft_ids) -> (Tensor, Tensor)")
+    lib.define("verify_prefix_bonus(Tensor logits, Tensor draft_ids) -> (Tensor, Tensor, Tensor, Tensor, Tensor)")
+    lib.define(
+        "verify_step(Tensor logits, Tensor draft_ids, int mode, float threshold, float temperature)"
+        " -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)"
+    )
+    lib.define("kv_append(Tensor base_k, Tensor base_v, Tensor new_k, Tensor new_v) -> (Tensor, Tensor)")
+    lib.define(
+        "kv_append_with_mask(Tensor base_k, Tensor base_v, Tensor draft_k, Tensor draft_v, Tensor accepted_mask,"
+        " Tensor accept_len) -> (Tensor, Tensor)"
+    )
+    lib.define(
+        "verify_attention(Tensor q, Tensor k_arena, Tensor v_arena, Tensor seq_lens, float scale, int max_seq_len)"
+        " -> Tensor"
+    )
+
+    def _verify_step_op(logits, draft_ids, mode, threshold, temperature):
+        name = {v: k for k, v in ACCEPT_MODES.items()}[int(mode)]
+        o = verify_step_cuda(logits, draft_ids, name, threshold, temperature)
+        return (o["accept_len"], o["accepted_mask"], o["target_ids"], o["bonus"], o["token_prob"], o["row_max"],
+                o["row_sumexp"])
+
+    def _kv_append_op(base_k, base_v, new_k, new_v):
+        # torch custom ops may not return views of their inputs: materialise the result
+        k, v = kv_append_cuda(base_k, base_v, new_k, new_v)
+        return k.clone(), v.clone()
+
+    def _kv_append_mask_op(base_k, base_v, draft_k, draft_v, accepted_mask, accept_len):
+        k, v = kv_append_with_mask_cuda(base_k, base_v, draft_k, draft_v, accepted_mask, accept_len)
+        return k.clone(), v.clone()
+
+    def _attn_op(q, k_arena, v_arena, seq_lens, scale, max_seq_len):
+        return verify_attention_cuda(q, k_arena, v_arena, seq_lens, scale if scale > 0 else None, max_seq_len)
+
+    lib.impl("verify_prefix", verify_prefix_cuda, "CUDA")
+    lib.impl("verify_prefix_bonus", verify_prefix_bonus_cuda, "CUDA")
+    lib.impl("verify_step", _verify_step_op, "CUDA")
+    lib.impl("kv_append", _kv_append_op, "CUDA")
+    lib.impl("kv_append_with_mask", _kv_append_mask_op, "CUDA")
+    lib.impl("verify_attention", _attn_op, "CUDA")
+    _TORCH_LIB = lib
+
+
+def set_verify_tuning(threads: int = 0, vectors_per_thread: int = 0) -> None:
+    _capi.lib().check(_capi.lib().sd_verify_set_tuning(threads, vectors_per_thread), "sd_verify_set_tuning")
+
+
+def set_kv_variant(variant: int = 0) -> None:
+    _capi.lib().check(_capi.lib().sd_kv_set_variant(variant), "sd_kv_set_variant")

@@ -1,0 +1,115 @@
+"""Preallocated KV-cache arena for every layer of one model, with device-side lengths.
+
+B200 data layout for the reference's KV state (``KVCache`` tuples grown by ``torch.cat``:
+src/specdec/cache/kv_types.py:14-31, src/specdec/cache/kv_cache_manager.py:194-199,:268-273):
+
+    k, v      [n_layers, B, Hkv, C, D]   one allocation each; C = capacity in rows
+    new_k/v   [n_layers, B, Hkv, R, D]   staging: the R = K+1 rows the verify forward produced
+    seq_lens  [B] int32 (device)         rows valid per sequence -- rollback is a length update
+
+One ``sd_kv_append`` launch (include/sd_verify.h) moves the accepted rows of every layer and
+zeroes the rejected slots, reading ``accept_len`` straight from the verify kernel's output buffer:
+O(R) bytes per (layer, sequence, head) instead of O(L), no host synchronisation
+(the reference synchronises the device after every append: src/specdec/models/hf_wrappers.py:1021-1022).
+"""
+
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from kernels import cuda_ops
+
+
+class KVArena:
+    def __init__(
+        self,
+        n_layers: int,
+        batch: int,
+        n_kv_heads: int,
+        head_dim: int,
+        capacity: int,
+        max_new_rows: int,
+        dtype: torch.dtype = torch.bfloat16,
+        device: str | torch.device = "cuda",
+    ) -> None:
+        self.n_layers, self.batch, self.n_kv_heads, self.head_dim = n_layers, batch, n_kv_heads, head_dim
+        self.capacity, self.max_new_rows = capacity, max_new_rows
+        self.dtype = dtype
+        self.device = torch.device(device)
+        shape = (n_layers, batch, n_kv_heads, capacity, head_dim)
+        self.k = torch.zeros(shape, dtype=dtype, device=self.device)
+        self.v = torch.zeros(shape, dtype=dtype, device=self.device)
+        stage = (n_layers, batch, n_kv_heads, max_new_rows, head_dim)
+        self.new_k = torch.zeros(stage, dtype=dtype, device=self.device)
+        self.new_v = torch.zeros(stage, dtype=dtype, device=self.device)
+        self.seq_lens = torch.zeros(batch, dtype=torch.int32, device=self.device)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.layer_table = self._build_table(self.new_k, self.new_v)
+        self._max_len_host = 0  # host-side upper bound of seq_lens, for the capacity check
+
+    # -- layout helpers -------------------------------------------------------------------------
+    def _build_table(self, new_k: torch.Tensor, new_v: torch.Tensor) -> torch.Tensor:
+        rows = [
+            [self.k[l].data_ptr(), self.v[l].data_ptr(), new_k[l].data_ptr(), new_v[l].data_ptr()]
+            for l in range(self.n_layers)
+        ]
+        return torch.tensor(rows, dtype=torch.int64).to(self.device)
+
+    @property
+    def row_bytes(self) -> int:
+        return self.head_dim * self.k.element_size()
+
+    def layer(self, l: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Full-capacity [B,Hkv,C,D] views of layer ``l`` (what the attention kernel reads)."""
+        return self.k[l], self.v[l]
+
+    def past_key_values(self, length: int):
+        """HF-style tuple of (k, v) [B,Hkv,length,D] views (reference: kv_types.py:62-86 slice_prefix)."""
+        return tuple((self.k[l][:, :, :length], self.v[l][:, :, :length]) for l in range(self.n_layers))
+
+    # -- state ------------------------------------------------------------------------------------
+    def set_lengths(self, lengths, max_len_host: Optional[int] = None) -> None:
+        lens = torch.as_tensor(lengths, dtype=torch.int32)
+        if max_len_host is None:
+            max_len_host = int(lens.max()) if lens.numel() else 0
+        self.seq_lens.copy_(lens.to(self.device), non_blocking=True)
+        self._max_len_host = max_len_host
+
+    def reset(self) -> None:
+        self.seq_lens.zero_()
+        self.overflow.zero_()
+        self._max_len_host = 0
+
+    # -- the hot call -----------------------------------------------------------------------------
+    def append(
+        self,
+        n_keep: Optional[torch.Tensor] = None,
+        keep_bias: int = 0,
+        zero_rejected: bool = True,
+        accepted_mask: Optional[torch.Tensor] = None,
+        rows: Optional[int] = None,
+        check_capacity: bool = True,
+    ) -> None:
+        """Append the staged rows of every layer.  ``n_keep`` [B] int32 (device) + ``keep_bias`` rows
+        of each sequence are kept (None = all ``rows``); lengths advance on device."""
+        R = self.max_new_rows if rows is None else rows
+        es = self.k.element_size()
+        cuda_ops.kv_arena_append_launch(
+            self.layer_table, self.n_layers, self.batch, self.n_kv_heads, R, self.row_bytes, self.capacity,
+            (self.k.stride(1) * es, self.k.stride(2) * es),
+            (self.new_k.stride(1) * es, self.new_k.stride(2) * es, self.new_k.stride(3) * es),
+            self.seq_lens, self.seq_lens, n_keep, keep_bias, accepted_mask, zero_rejected,
+            self._max_len_host if check_capacity else -1, self.overflow, self._ticket,
+        )
+        self._max_len_host = min(self.capacity, self._max_len_host + R)
+
+    def step_bytes(self, mean_keep: float, rows: Optional[int] = None, zero_rejected: bool = True) -> int:
+        """Algorithmic bytes of one append: accepted rows read, offered rows
+        written (or accepted rows only when rejected slots are not zeroed)."""
+        R = self.max_new_rows if rows is None else rows
+        unit = self.n_layers * 2 * self.batch * self.n_kv_heads * self.row_bytes
+        written = R if zero_rejected else mean_keep
+        return int(unit * (mean_keep + written))

@@ -1,0 +1,95 @@
+"""The batched verify step: fused verify -> kv_append, device-resident, CUDA-graph capturable.
+
+Replaces the per-sequence host loop of the reference's batch path
+(src/specdec/core/pipeline.py:2958-3620: one ``policy.accept_tokens`` + ``.item()`` per sequence,
+bonus-token selection :3140-3362, then ``realign_kv_cache`` :3636-3646) for the part that is
+arithmetic: all sequences are verified by ONE kernel launch, the accepted KV rows of all layers are
+appended by ONE more, and only a packed [B, K+2] int32 record ever needs to reach the host.
+
+Static buffers (graph replay needs fixed addresses):
+    logits     [B, K+1, V]   target logits of the teacher-forced pass (producer: the target model)
+    draft_ids  [B, K]        draft tokens
+    accept_len [B] i32, accepted_mask [B,K] u8, target_ids [B,K+1] i32, bonus [B] i32,
+    packed     [B, K+2] i32  {accept_len, target_ids}  -> allgather / D2H record
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from kernels import _capi, cuda_ops
+from specdec.cache.kv_arena import KVArena
+
+
+class VerifyStep:
+    def __init__(
+        self,
+        batch: int,
+        k_draft: int,
+        vocab: int,
+        arena: Optional[KVArena] = None,
+        logits_dtype: torch.dtype = torch.bfloat16,
+        id_dtype: torch.dtype = torch.int64,
+        device: str | torch.device = "cuda",
+        mode: str = "greedy",
+        threshold: float = 0.0,
+        temperature: float = 1.0,
+    ) -> None:
+        self.B, self.K, self.V = batch, k_draft, vocab
+        self.device = torch.device(device)
+        self.arena = arena
+        self.mode, self.threshold, self.temperature = mode, threshold, temperature
+        dev = self.device
+        self.logits = torch.zeros((batch, k_draft + 1, vocab), dtype=logits_dtype, device=dev)
+        self.draft_ids = torch.zeros((batch, k_draft), dtype=id_dtype, device=dev)
+        self.accept_len = torch.zeros(batch, dtype=torch.int32, device=dev)
+        self.accepted_mask = torch.zeros((batch, k_draft), dtype=torch.uint8, device=dev)
+        self.target_ids = torch.zeros((batch, k_draft + 1), dtype=torch.int32, device=dev)
+        self.bonus = torch.zeros(batch, dtype=torch.int32, device=dev)
+        self.packed = torch.zeros((batch, k_draft + 2), dtype=torch.int32, device=dev)
+        self.token_prob = torch.zeros((batch, k_draft), dtype=torch.float32, device=dev) if mode != "greedy" else None
+        self.row_max = torch.zeros((batch, k_draft + 1), dtype=torch.float32, device=dev) if mode != "greedy" else None
+        self.row_sumexp = torch.zeros_like(self.row_max) if mode != "greedy" else None
+        need = int(_capi.lib().sd_verify_workspace_bytes(batch, k_draft + 1))
+        self.workspace = torch.zeros(need, dtype=torch.uint8, device=dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = 1 + (1 if arena is not None else 0)
+
+    # -- eager ------------------------------------------------------------------------------------
+    def run(self, logits: Optional[torch.Tensor] = None, draft_ids: Optional[torch.Tensor] = None) -> None:
+        """Enqueue verify (+ append) on the current stream.  ``logits``/``draft_ids`` default to the
+        static buffers; passing other tensors verifies them in place (no copy)."""
+        lg = self.logits if logits is None else logits
+        ids = self.draft_ids if draft_ids is None else draft_ids
+        cuda_ops.verify_launch(
+            lg, ids, self.accept_len, self.accepted_mask, self.target_ids, self.bonus, self.packed, self.workspace,
+            mode=cuda_ops.ACCEPT_MODES[self.mode], threshold=self.threshold, inv_temperature=1.0 / self.temperature,
+            token_prob=self.token_prob, row_max=self.row_max, row_sumexp=self.row_sumexp,
+            stats=self.mode != "greedy",
+        )
+        if self.arena is not None:
+            # keep accept_len drafts + the token they were conditioned on (row 0 of the pass)
+            self.arena.append(self.accept_len, keep_bias=1, zero_rejected=True, check_capacity=False)
+
+    # -- CUDA graph (reference: src/specdec/utils/graph_capture.py:49-99 GraphCapture, never wired in) --
+    def capture(self) -> None:
+        torch.cuda.synchronize(self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self.run()  # warm-up outside capture (module load, attribute setup)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        if self.arena is not None:
+            self._lens_before_capture = self.arena.seq_lens.clone()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run()
+        self.graph = g
+
+    def replay(self) -> None:
+        if self.graph is None:
+            raise RuntimeError("capture() first")
+        self.graph.replay()

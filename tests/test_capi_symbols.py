@@ -1,0 +1,64 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/sd_verify.h
+declares.  No compute calls (no GPU here)."""
+import ctypes
+import subprocess
+
+import pytest
+
+from kernels import _capi, build
+
+
+def test_library_builds_and_is_current():
+    path = build.build_cuda_kernels()
+    assert path.exists() and path.stat().st_size > 0
+    assert build.is_current()
+    assert build.get_cuda_arch() == "sm_100a"
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    declared = _capi.declared_symbols()
+    assert len(declared) >= 12
+    cdll = ctypes.CDLL(str(build.LIB_PATH))
+    for name in declared:
+        assert hasattr(cdll, name), f"{name} declared in include/sd_verify.h but not exported"
+    assert sorted(_capi.SIGNATURES) == declared, "ctypes binding and header disagree"
+
+
+def test_abi_version_and_error_strings():
+    lib = _capi.lib()
+    assert lib.sd_abi_version() == _capi.ABI_VERSION
+    assert lib.sd_error_string(0) == b"ok"
+    assert b"workspace" in lib.sd_error_string(-3)
+    assert lib.sd_verify_workspace_bytes(64, 5) >= 64 * 5 * 64 * 8
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    lib = _capi.lib()
+    # rows must be K or K+1 -> SD_ERR_SHAPE, detected before any CUDA call
+    rc = lib.sd_verify_prefix(1, _capi.DTYPE_BF16, 0, 0, 1, _capi.ID_I64, 0, 1, None, None, None, None, 1, 1 << 30,
+                              2, 7, 4, 100, None)
+    assert rc == -2
+    rc = lib.sd_verify_prefix(None, _capi.DTYPE_BF16, 0, 0, 1, _capi.ID_I64, 0, 1, None, None, None, None, 1, 1 << 30,
+                              2, 5, 4, 100, None)
+    assert rc == -1
+    assert lib.sd_verify_set_tuning(100, 3) == -1
+    assert lib.sd_verify_set_tuning(0, 0) == 0
+    assert lib.sd_kv_set_variant(7) == -1
+    # capacity check on host-known sizes
+    rc = lib.sd_kv_append(1, 1, 1, 1, 5, 256, 8, 0, 0, 0, 0, 0, None, None, None, 0, None, 1, 4, None, 1, None)
+    assert rc == -6
+
+
+def test_sass_is_sm100a_and_uses_128bit_loads_and_tma():
+    """cuobjdump evidence checked here so a wrong -gencode is caught on CPU."""
+    out = subprocess.run(["cuobjdump", "-lelf", str(build.LIB_PATH)], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+    sass = subprocess.run(["cuobjdump", "-sass", str(build.LIB_PATH)], capture_output=True, text=True).stdout
+    import re
+
+    assert re.search(r"LDG\.E[.A-Z]*\.128", sass), "128-bit global loads expected in the verify kernel"
+    assert "HMNMX2.BF16_V2.NAN" in sass  # packed NaN-propagating bf16x2 max
+    assert "REDUX.MAX" in sass           # warp reduce in hardware
+    assert "UBLKCP" in sass  # cp.async.bulk (TMA 1-D) in the kv_append bulk variant

@@ -1,0 +1,105 @@
+"""CPU: the registry keeps the reference's API and dispatch rules
+(reference tests: tests/test_kernel_registry.py, tests/test_kernels_verify.py:131-154)."""
+import pytest
+import torch
+
+import kernels
+from kernels.registry import KernelRegistry
+
+
+@pytest.fixture()
+def clean_registry():
+    saved = {k: list(v) for k, v in KernelRegistry._kernels.items()}
+    KernelRegistry._kernels.clear()
+    yield KernelRegistry
+    KernelRegistry._kernels.clear()
+    KernelRegistry._kernels.update(saved)
+
+
+def test_priority_and_device_filter(clean_registry):
+    R = clean_registry
+
+    def cuda_kernel():
+        return "cuda"
+
+    def triton_kernel():
+        return "triton"
+
+    def torch_kernel():
+        return "torch"
+
+    R.register("test_op", torch_kernel, priority=10, device="auto")
+    R.register("test_op", cuda_kernel, priority=100, device="cuda")
+    R.register("test_op", triton_kernel, priority=50, device="cuda")
+    assert R.get_best("test_op", "cuda") is cuda_kernel
+    assert R.get_best("test_op", "cpu") is torch_kernel
+    assert R.get_best("test_op", "mps") is torch_kernel
+    assert R.get_best("unknown_op", "cuda") is None
+    listed = R.list_available("test_op", "cuda")
+    assert [e["name"] for e in listed] == ["cuda_kernel", "triton_kernel", "torch_kernel"]
+    assert listed[0]["priority"] == 100
+    assert R.list_available("unknown_op", "cuda") == []
+    assert R.get_status("cuda") == {"test_op": "cuda_kernel"}
+    assert R.get_status("cpu") == {"test_op": "torch_kernel"}
+
+
+def test_reregistration_replaces(clean_registry):
+    R = clean_registry
+
+    def k():
+        return 1
+
+    R.register("op", k, 10, "cuda")
+    R.register("op", k, 70, "cuda")
+    assert len(R.list_available("op", "cuda")) == 1
+    assert R.list_available("op", "cuda")[0]["priority"] == 70
+
+
+def test_package_surface_matches_reference():
+    for name in ("verify_prefix", "kv_append", "get_verify_prefix", "get_kv_append", "get_kernel_info",
+                 "log_kernel_status", "registry"):
+        assert hasattr(kernels, name)
+    info = kernels.get_kernel_info()
+    for key in ("verify_backend", "kv_append_backend", "verify_available", "kv_append_available", "device"):
+        assert key in info
+    assert info["verify_backend"] in ("cuda", "triton", "torch", "fallback", "unknown")
+    status = kernels.registry.get_status("cuda")
+    assert status["verify_prefix"] == "verify_prefix_cuda" and status["kv_append"] == "kv_append_cuda"
+    # every registered name reads as the "cuda" backend under the reference's name sniffing
+    assert all("cuda" in n and "triton" not in n for n in status.values())
+
+
+def test_no_cpu_fallback_is_registered():
+    """Product path has no CPU / PyTorch implementation: CPU lookups return None and calls raise."""
+    assert kernels.registry.get_best("verify_prefix", "cpu") is None
+    assert kernels.registry.get_best("kv_append", "cpu") is None
+    fn = kernels.registry.get_best("verify_prefix", "cuda")
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        fn(torch.zeros(1, 2, 8), torch.zeros(1, 2, dtype=torch.long))
+    with pytest.raises(NotImplementedError):
+        torch.ops.sd_b200.verify_prefix(torch.zeros(1, 2, 8), torch.zeros(1, 2, dtype=torch.long))
+    kv = kernels.registry.get_best("kv_append", "cuda")
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        kv(torch.zeros(1, 1, 2, 4), torch.zeros(1, 1, 2, 4), torch.zeros(1, 1, 1, 4), torch.zeros(1, 1, 1, 4))
+
+
+def test_shape_errors_match_reference_before_device_checks():
+    fn = kernels.registry.get_best("verify_prefix", "cuda")
+    with pytest.raises(AssertionError):
+        fn(torch.zeros(2, 3, 8), torch.zeros(2, 2, dtype=torch.long))
+    with pytest.raises(AssertionError):
+        fn(torch.zeros(3, 8), torch.zeros(3, dtype=torch.long))
+    kv = kernels.registry.get_best("kv_append", "cuda")
+    a = torch.zeros(2, 2, 3, 4)
+    for bad in (torch.zeros(1, 2, 2, 4), torch.zeros(2, 4, 2, 4), torch.zeros(2, 2, 2, 8)):
+        with pytest.raises(AssertionError):
+            kv(a, a, bad, bad)
+
+
+def test_product_package_does_not_import_the_oracle():
+    import pathlib
+
+    pkg = pathlib.Path(kernels.__file__).resolve().parent.parent
+    for py in pkg.rglob("*.py"):
+        text = py.read_text()
+        assert "import oracle" not in text and "from oracle" not in text, py

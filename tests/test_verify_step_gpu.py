@@ -1,0 +1,95 @@
+"""GPU: the batched verify step (verify -> kv_append), eager and as a replayed CUDA graph."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from specdec.cache.kv_arena import KVArena
+from specdec.verify_step import VerifyStep
+from helpers import make_verify_inputs, to_np
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(B=6, K=4, V=50257, layers=3, H=2, D=64, L=9, cap=80):
+    dev = torch.device("cuda")
+    arena = KVArena(layers, B, H, D, cap, K + 1, torch.bfloat16, dev)
+    g = torch.Generator().manual_seed(1)
+    arena.k[:, :, :, :L] = torch.randn(layers, B, H, L, D, generator=g).to(torch.bfloat16).cuda()
+    arena.v[:, :, :, :L] = torch.randn(layers, B, H, L, D, generator=g).to(torch.bfloat16).cuda()
+    arena.set_lengths([L] * B)
+    step = VerifyStep(B, K, V, arena=arena, device=dev)
+    return step, arena, g
+
+
+def _oracle_step(exp_k, exp_v, lens, logits, ids, nk, nv):
+    acc, mask, tgt, bonus = c_oracle.verify(to_np(logits), "bf16", to_np(ids))
+    for l in range(exp_k.shape[0]):
+        new_lens = c_oracle.kv_arena_append(exp_k[l], lens, nk[l], acc + 1, True)
+        c_oracle.kv_arena_append(exp_v[l], lens, nv[l], acc + 1, True)
+    return acc, mask, tgt, bonus, new_lens
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_multi_step_matches_oracle(use_graph):
+    step, arena, g = _setup()
+    exp_k, exp_v = to_np(arena.k).copy(), to_np(arena.v).copy()
+    lens = arena.seq_lens.cpu().numpy().copy()
+    if use_graph:
+        step.capture()
+        arena.set_lengths(lens)          # capture's warm-up run advanced the lengths
+        arena.k.copy_(torch.from_numpy(exp_k.view(np.int16)).view(torch.bfloat16))
+        arena.v.copy_(torch.from_numpy(exp_v.view(np.int16)).view(torch.bfloat16))
+    for it in range(6):
+        logits, ids = make_verify_inputs(step.B, step.K + 1, step.K, step.V, "bf16", p_match=0.7, seed=50 + it)
+        step.logits.copy_(logits)
+        step.draft_ids.copy_(ids)
+        arena.new_k.copy_(torch.randn(arena.new_k.shape, generator=g).to(torch.bfloat16))
+        arena.new_v.copy_(torch.randn(arena.new_v.shape, generator=g).to(torch.bfloat16))
+        step.replay() if use_graph else step.run()
+        torch.cuda.synchronize()
+        acc, mask, tgt, bonus, lens = _oracle_step(exp_k, exp_v, lens, logits, ids, to_np(arena.new_k), to_np(arena.new_v))
+        np.testing.assert_array_equal(step.accept_len.cpu().numpy(), acc)
+        np.testing.assert_array_equal(step.accepted_mask.cpu().numpy(), mask)
+        np.testing.assert_array_equal(step.target_ids.cpu().numpy(), tgt)
+        np.testing.assert_array_equal(step.bonus.cpu().numpy(), bonus)
+        np.testing.assert_array_equal(step.packed.cpu().numpy()[:, 0], acc)
+        np.testing.assert_array_equal(arena.seq_lens.cpu().numpy(), lens)
+        np.testing.assert_array_equal(to_np(arena.k), exp_k)
+        np.testing.assert_array_equal(to_np(arena.v), exp_v)
+
+
+def test_sampling_mode_step():
+    dev = torch.device("cuda")
+    step = VerifyStep(4, 3, 5000, arena=None, device=dev, mode="typical", threshold=0.2, temperature=0.7)
+    logits, ids = make_verify_inputs(4, 4, 3, 5000, "bf16", p_match=0.6, seed=9)
+    step.logits.copy_(logits)
+    step.draft_ids.copy_(ids)
+    step.run()
+    torch.cuda.synchronize()
+    from oracle import specdec_oracle as O
+
+    x = O.as_f32(to_np(logits), "bf16") / np.float32(0.7)
+    e_acc, e_prob = O.accept_typical(x[:, :3], to_np(ids), 0.2)
+    np.testing.assert_allclose(step.token_prob.cpu().numpy(), e_prob, rtol=5e-4, atol=1e-6)
+    if not (np.abs(e_prob - 0.2) < 1e-3).any():
+        np.testing.assert_array_equal(step.accept_len.cpu().numpy(), e_acc)
+
+
+def test_advance_sequences_on_device_from_packed():
+    from scheduler.batch_shard import advance_sequences
+
+    step, arena, g = _setup(B=5, K=4, V=3000, layers=1, H=1, D=16)
+    logits, ids = make_verify_inputs(5, 5, 4, 3000, "bf16", p_match=0.8, seed=4)
+    step.logits.copy_(logits)
+    step.draft_ids.copy_(ids)
+    step.run()
+    tokens = torch.zeros(5, 32, dtype=torch.int64, device="cuda")
+    lengths = torch.tensor([3, 4, 5, 6, 7], device="cuda")
+    new_len, n_new = advance_sequences(tokens, lengths, step.packed)
+    acc, _, tgt, bonus = c_oracle.verify(to_np(logits), "bf16", to_np(ids))
+    assert n_new.cpu().tolist() == (acc + 1).tolist()
+    for b in range(5):
+        got = tokens[b, int(lengths[b]) : int(new_len[b])].cpu().tolist()
+        assert got == tgt[b, : acc[b] + 1].tolist() and got[-1] == bonus[b]
+        assert got[:-1] == to_np(ids)[b, : acc[b]].tolist()  # accepted tokens are the draft tokens

@@ -1,0 +1,117 @@
+#!/usr/bin/env python3
+"""Sweep launch configurations of the fused verify kernel (and kv_append variants) on one GPU.
+
+    python tools/sweep_verify.py [--B 64] [--K 4] [--V 128256] [--iters 200]
+
+Prints one line per configuration: microseconds per launch (CUDA events around graph replays over
+rotating input buffers, so reads come from HBM, not the 126 MB L2) and achieved GB/s."""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(ROOT / "llm-inference-lab_b200"), str(ROOT)]
+
+import torch  # noqa: E402
+
+from kernels import cuda_ops  # noqa: E402
+from specdec.cache.kv_arena import KVArena  # noqa: E402
+from specdec.verify_step import VerifyStep  # noqa: E402
+
+
+def time_graphs(fns, iters, warm=20):
+    side = torch.cuda.Stream()
+    graphs = []
+    for fn in fns:
+        fn()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        for fn in fns:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                fn()
+            graphs.append(g)
+    torch.cuda.synchronize()
+    for i in range(warm):
+        graphs[i % len(graphs)].replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(iters):
+        graphs[i % len(graphs)].replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters * 1e3  # us
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--B", type=int, default=64)
+    ap.add_argument("--K", type=int, default=4)
+    ap.add_argument("--V", type=int, default=128256)
+    ap.add_argument("--iters", type=int, default=200)
+    ap.add_argument("--nbuf", type=int, default=4)
+    ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--skip-kv", action="store_true")
+    ap.add_argument("--stats", action="store_true")
+    args = ap.parse_args()
+    dev = torch.device("cuda")
+    dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
+    B, K, V = args.B, args.K, args.V
+    steps = []
+    for i in range(args.nbuf):
+        st = VerifyStep(B, K, V, arena=None, device=dev, logits_dtype=dt, mode="typical" if args.stats else "greedy",
+                        threshold=0.3)
+        st.logits.copy_(torch.randn(B, K + 1, V, device=dev).to(dt))
+        st.draft_ids.copy_(torch.randint(0, V, (B, K), device=dev))
+        steps.append(st)
+    nbytes = B * (K + 1) * V * steps[0].logits.element_size()
+    results = []
+    configs = [(0, 0)] + [(t, v) for t in (128, 256, 512) for v in (1, 2, 4, 8, 16)]
+    for (t, v) in configs:
+        try:
+            cuda_ops.set_verify_tuning(t, v)
+            us = time_graphs([s.run for s in steps], args.iters)
+            results.append({"kernel": "verify", "threads": t, "vpt": v, "us": us, "GBps": nbytes / us / 1e3})
+            print(json.dumps(results[-1]), flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(json.dumps({"kernel": "verify", "threads": t, "vpt": v, "error": str(e)[:200]}), flush=True)
+    cuda_ops.set_verify_tuning(0, 0)
+    # torch.argmax on the same buffers: the ATen incumbent (reference.py:37 on CUDA tensors)
+    us = time_graphs([lambda s=s: torch.argmax(s.logits, dim=-1) for s in steps], args.iters)
+    print(json.dumps({"kernel": "torch.argmax", "us": us, "GBps": nbytes / us / 1e3}), flush=True)
+    # copy peak on this box, same method as MEASURED_PEAKS (read+write bytes)
+    src = [s.logits for s in steps]
+    dst = [torch.empty_like(s.logits) for s in steps[:2]]
+    us = time_graphs([lambda i=i: dst[i % 2].copy_(src[i]) for i in range(args.nbuf)], args.iters)
+    print(json.dumps({"kernel": "torch.copy_", "us": us, "GBps": 2 * nbytes / us / 1e3}), flush=True)
+
+    if not args.skip_kv:
+        layers, H, D, R, L = 28, 8, 128, K + 1, 1024
+        arena = KVArena(layers, B, H, D, L + R * (args.iters + 64) * 2, R, torch.bfloat16, dev)
+        stages = [(torch.randn(arena.new_k.shape, device=dev).to(torch.bfloat16), torch.randn(arena.new_v.shape, device=dev).to(torch.bfloat16))
+                  for _ in range(args.nbuf)]
+        tables = [arena._build_table(k, v) for k, v in stages]
+        accept = torch.randint(0, K + 1, (B,), device=dev, dtype=torch.int32)
+        mean_keep = float((accept + 1).float().mean())
+        for variant in (1, 2):
+            for zero in (True, False):
+                cuda_ops.set_kv_variant(variant)
+                arena.set_lengths([L] * B)
+
+                def mk(i):
+                    def f():
+                        arena.layer_table = tables[i]
+                        arena.append(accept, keep_bias=1, zero_rejected=zero, check_capacity=False)
+                    return f
+
+                us = time_graphs([mk(i) for i in range(args.nbuf)], args.iters)
+                nb = arena.step_bytes(mean_keep, R, zero)
+                print(json.dumps({"kernel": "kv_append", "variant": variant, "zero_rejected": zero, "us": us,
+                                  "GBps": nb / us / 1e3, "bytes": nb, "mean_keep": mean_keep}), flush=True)
+        cuda_ops.set_kv_variant(0)
+
+
+if __name__ == "__main__":
+    main()
