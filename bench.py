@@ -198,7 +198,7 @@ def workload_config(args, world):
         "batch_per_gpu": args.batch, "global_batch": args.batch * world, "K": CFG["K"], "V": CFG["V"],
         "layers": CFG["layers"], "kv_heads": CFG["Hkv"], "head_dim": CFG["D"], "context_len": CFG["L"],
         "planted_acceptance": CFG["p_match"], "parallelism": f"batch-sharded dp{world}",
-        "l2_policy": f"inputs rotate over {CFG['nbuf']} buffer sets ({CFG['nbuf']} x 82 MB logits + {CFG['nbuf']} x 73 MB KV rows "
+        "l2_policy": f"inputs rotate over {CFG['nbuf']} buffer sets ({CFG['nbuf']} x 82 MB logits + {CFG['nbuf']} x 37 MB KV rows "
                      "> 126 MB L2) so every replay reads from HBM",
     }
 
