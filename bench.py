@@ -8,7 +8,7 @@
 Metric (BASELINE.json): verify-step tokens/s at B=64 per GPU, K=4, V=128256 (Llama-3.2 vocabulary),
 bf16 logits, kv_append of the accepted rows for the 28 layers of Llama-3.2-3B (Hkv=8, D=128).
 One step = fused verify over [B, K+1, V] logits + kv_append for all layers (+ the all-gather of the
-packed [B, K+2] records when N > 1), replayed as one CUDA graph.
+packed [B, K+2] records when N > 1), replayed from CUDA graphs (4 consecutive steps per graph).
 tokens/s = (sum_b accept_len[b] + B) / t_step   (accepted drafts + one bonus token per sequence).
 
 The JSON line follows the driver contract and adds `roofline` (dominant kernel: fused verify),
@@ -36,7 +36,7 @@ UNIT = "tokens/s"
 SEED = 1234  # the reference's default seed (src/specdec/core/pipeline.py:407)
 
 # configs[2] of BASELINE.json: Llama-3.2-3B target (28 layers, 8 KV heads, head_dim 128, V=128256)
-CFG = dict(B=64, K=4, V=128256, layers=28, Hkv=8, D=128, L=1024, p_match=0.8, nbuf=4)
+CFG = dict(B=64, K=4, V=128256, layers=28, Hq=24, Hkv=8, D=128, L=1024, p_match=0.8, nbuf=4)
 
 
 def parse_args():
@@ -51,6 +51,16 @@ def parse_args():
     ap.add_argument("--kv-variant", type=int, default=0)
     ap.add_argument("--batch", type=int, default=CFG["B"], help="sequences per GPU")
     return ap.parse_args()
+
+
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py); empty if no capture is committed."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        return {k: v.get("dram_bytes") for k, v in json.loads(p.read_text()).items()}
+    except Exception:
+        return {}
 
 
 def load_peaks():
@@ -259,19 +269,37 @@ def run_ours(args):
         if exch is not None:
             exch.all_gather(st.packed)
 
-    # warm every buffer set eagerly, then capture one graph per set
+    # warm every buffer set eagerly, then capture (a) one graph per buffer set and (b) one GROUP graph
+    # holding NB consecutive steps (set 0..NB-1): inside a graph the kernels are linked by programmatic
+    # dependent-launch edges, so a kernel's launch latency overlaps the tail of its predecessor.  The
+    # timed region replays the group graph steps // NB times and single-step graphs for the remainder.
     for i in range(NB):
         one_step(i)
     torch.cuda.synchronize()
-    graphs = []
     side = torch.cuda.Stream(dev)
-    with torch.cuda.stream(side):
-        for i in range(NB):
+
+    def capture(fn_list):
+        with torch.cuda.stream(side):
             gr = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gr, stream=side):
-                one_step(i)
-            graphs.append(gr)
-    torch.cuda.synchronize()
+                for fn in fn_list:
+                    fn()
+        return gr
+
+    def make_runner(fn_of_i):
+        """Returns run(n): n launches of fn_of_i over the rotating buffer sets."""
+        singles = [capture([lambda i=i: fn_of_i(i)]) for i in range(NB)]
+        group = capture([lambda i=i: fn_of_i(i) for i in range(NB)])
+        torch.cuda.synchronize()
+
+        def run(n):
+            for _ in range(n // NB):
+                group.replay()
+            for s in range(n % NB):
+                singles[s].replay()
+        return run
+
+    run_steps = make_runner(one_step)
     arena.set_lengths([CFG["L"]] * B)
 
     def barrier():
@@ -279,38 +307,27 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for s in range(args.warmup):
-        graphs[s % NB].replay()
+    run_steps(args.warmup)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     ev0.record()
-    for s in range(args.steps):
-        graphs[s % NB].replay()
+    run_steps(args.steps)
     ev1.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     step_ms = ev0.elapsed_time(ev1) / args.steps
 
     # ---- kernel-isolation loops for the roofline (same buffers, same rotation, CUDA events) ----
-    def isolate(fn, n_launch):
-        grs = []
-        with torch.cuda.stream(side):
-            for i in range(NB):
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr, stream=side):
-                    fn(i)
-                grs.append(gr)
-        torch.cuda.synchronize()
-        for s in range(max(3, args.warmup)):
-            grs[s % NB].replay()
+    def isolate(fn_of_i, n_launch):
+        run = make_runner(fn_of_i)
+        run(max(NB, args.warmup))
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for s in range(n_launch):
-            grs[s % NB].replay()
+        run(n_launch)
         b.record()
         torch.cuda.synchronize()
         return a.elapsed_time(b) / n_launch
@@ -322,6 +339,18 @@ def run_ours(args):
     verify_ms = isolate(lambda i: steps[i].run(), args.steps)
     arena.set_lengths([CFG["L"]] * B)
     kv_ms = isolate(kv_only, args.steps)
+
+    # verify attention (kernel 3), one layer per launch, rotating over the arena's layers so that the
+    # 2 x 134 MB of K/V per launch come from HBM; lengths pinned at L (the arena's own lengths moved)
+    Hq = CFG["Hq"]
+    attn_q = [torch.randn(B, Hq, R, CFG["D"], generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16) for _ in range(NB)]
+    attn_out = torch.empty_like(attn_q[0])
+    attn_lens = torch.full((B,), CFG["L"], dtype=torch.int32, device=dev)
+    attn_ws = torch.empty(int(cuda_ops._capi.lib().sd_verify_attention_workspace_bytes(B, Hq, R, CFG["D"], 0)),
+                          dtype=torch.uint8, device=dev)
+    attn_ms = isolate(lambda i: cuda_ops.verify_attention_cuda(
+        attn_q[i], arena.k[i * 5 % CFG["layers"]], arena.v[i * 5 % CFG["layers"]], attn_lens, max_seq_len=CFG["L"],
+        out=attn_out, workspace=attn_ws), args.steps)
     clocks = sampler.stop()
 
     acc_sum = [int(steps[i].accept_len.sum().item()) for i in range(NB)]
@@ -333,6 +362,7 @@ def run_ours(args):
     e2e = None
     if e2e_steps:
         arena.set_lengths([CFG["L"]] * B)
+        e2e_graph = capture([lambda: one_step(0)])
         h_logits = [steps[i].logits.cpu().pin_memory() for i in range(2)]
         h_ids = [steps[i].draft_ids.cpu().pin_memory() for i in range(2)]
         h_k = [stage_k[i].cpu().pin_memory() for i in range(2)]
@@ -347,7 +377,7 @@ def run_ours(args):
             steps[0].draft_ids.copy_(h_ids[i], non_blocking=True)
             stage_k[0].copy_(h_k[i], non_blocking=True)
             stage_v[0].copy_(h_v[i], non_blocking=True)
-            graphs[0].replay()
+            e2e_graph.replay()
             h_out.copy_(steps[0].packed, non_blocking=True)
             torch.cuda.current_stream().synchronize()  # the caller needs the record to advance sequences
             return int(h_out[:, 0].sum()) + B
@@ -365,9 +395,9 @@ def run_ours(args):
 
     # ---- reduce over ranks: max time, summed tokens ----
     if world > 1:
-        t = torch.tensor([step_ms, verify_ms, kv_ms, e2e["seconds"] if e2e else 0.0], device=dev, dtype=torch.float64)
+        t = torch.tensor([step_ms, verify_ms, kv_ms, attn_ms, e2e["seconds"] if e2e else 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms, verify_ms, kv_ms, e2e_s = (float(x) for x in t.tolist())
+        step_ms, verify_ms, kv_ms, attn_ms, e2e_s = (float(x) for x in t.tolist())
         c = torch.tensor([tokens_per_step, float(e2e["tokens"]) if e2e else 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         tokens_per_step_all, e2e_tokens_all = (float(x) for x in c.tolist())
@@ -382,6 +412,10 @@ def run_ours(args):
         kv_bytes = arena.step_bytes(mean_keep, R, True)
         v_gbs = verify_bytes / (verify_ms * 1e-3) / 1e9
         kv_gbs = kv_bytes / (kv_ms * 1e-3) / 1e9
+        attn_bytes = 2 * B * CFG["Hkv"] * (CFG["L"] + R) * CFG["D"] * 2 + 2 * B * CFG["Hq"] * R * CFG["D"] * 2
+        attn_flops = 4 * B * CFG["Hq"] * R * (CFG["L"] + R) * CFG["D"]
+        attn_gbs = attn_bytes / (attn_ms * 1e-3) / 1e9
+        traffic = load_traffic()
         line = {
             "metric": METRIC, "value": tokens_per_step_all / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
@@ -392,11 +426,16 @@ def run_ours(args):
             "gpu_launches": args.steps * 2,
             "launches_per_step": {"sd_verify_kernel": 1, "sd_kv_append_kernel": 1, "nccl_allgather": 1 if world > 1 else 0},
             "roofline": {"bound": "hbm", "kernel": "verify_kernel<bf16>", "achieved": v_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": v_gbs / peak, "frac_of_8TBs_nominal": v_gbs / 8000.0, "traffic": None,
+                         "frac": v_gbs / peak, "frac_of_8TBs_nominal": v_gbs / 8000.0, "traffic": traffic.get("verify_kernel"),
                          "algorithmic_bytes": verify_bytes, "us_per_launch": verify_ms * 1e3, "peak_source": peak_src},
             "roofline_kv": {"bound": "hbm", "kernel": "kv_append_kernel", "achieved": kv_gbs, "peak": peak, "unit": "GB/s",
                             "frac": kv_gbs / peak, "algorithmic_bytes": kv_bytes, "us_per_launch": kv_ms * 1e3,
-                            "mean_rows_kept": mean_keep},
+                            "mean_rows_kept": mean_keep, "traffic": traffic.get("kv_append_kernel")},
+            "roofline_attn": {"bound": "hbm", "kernel": "verify_attn_kernel<bf16,D=128> (one layer per launch, mma.sync m16n8k16)",
+                              "achieved": attn_gbs, "peak": peak, "unit": "GB/s", "frac": attn_gbs / peak,
+                              "algorithmic_bytes": attn_bytes, "us_per_launch": attn_ms * 1e3,
+                              "tflops": attn_flops / (attn_ms * 1e-3) / 1e12, "traffic": traffic.get("verify_attn_kernel"),
+                              "config": {"B": B, "Hq": CFG["Hq"], "Hkv": CFG["Hkv"], "R": R, "D": CFG["D"], "context_len": CFG["L"]}},
             "step_hbm_frac": (verify_bytes + kv_bytes) / (step_ms * 1e-3) / 1e9 / peak,
             "clocks": clocks, "wall_s_timed_region": t_wall,
         }

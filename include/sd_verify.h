@@ -54,6 +54,10 @@ enum sd_accept_mode {
 
 int sd_abi_version(void);
 const char* sd_error_string(int code);
+/* Programmatic dependent launch for every kernel of the library (default on; env SD_B200_PDL=0 turns
+ * it off): a kernel's CTAs may become resident while the previous kernel on the stream drains, and
+ * block in griddepcontrol.wait until it has completed.  Capturable in CUDA graphs. */
+int sd_set_pdl(int enabled);
 /* Fills SM count and compute capability of the current device.  Returns 0 or a cudaError_t. */
 int sd_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -116,6 +120,9 @@ int sd_verify_step(const void* logits, int logit_dtype, int64_t stride_b, int64_
 /* Tuning hook used by tools/ and bench.py sweeps: threads per CTA (128..1024, multiple of 32),
  * 16-byte vectors in flight per thread (1..16), 0 restores the built-in heuristic. */
 int sd_verify_set_tuning(int threads, int vectors_per_thread);
+/* Kernel variant (evidence runs): 1 = persistent grid with equal contiguous unit ranges (default),
+ * 0 = one CTA per (row, chunk).  ctas_per_sm caps the persistent grid (0 = occupancy limit). */
+int sd_verify_set_variant(int variant, int ctas_per_sm);
 
 /* ------------------------------------------------------------------------------------------
  * Kernel 2: kv_append into a preallocated arena, with rollback of rejected slots.
@@ -180,7 +187,8 @@ int sd_kv_append_layer(void* arena_k, void* arena_v, const void* new_k, const vo
                        const uint8_t* accepted_mask, int zero_rejected, int32_t* ticket, void* stream);
 
 /* Variant selector for sd_kv_append (evidence runs): 0 = heuristic, 1 = 128-bit LDG/STG kernel,
- * 2 = cp.async.bulk (TMA 1-D) shared-memory staged kernel. */
+ * 2 = cp.async.bulk (TMA 1-D) shared-memory staged kernel, 3 = column kernel (one thread per 16-byte
+ * column, all R rows of K and V in flight). */
 int sd_kv_set_variant(int variant);
 
 /* ------------------------------------------------------------------------------------------
@@ -191,7 +199,10 @@ int sd_kv_set_variant(int variant);
  * (src/specdec/models/hf_wrappers.py:98 attn_implementation="sdpa";
  *  src/scheduler/speculative_scheduler.py:192-199 K greedy steps), with ONE pass over the KV cache.
  *
- * q        [B, Hq, R, D]   contiguous, dtype f16/bf16; R = K+1 <= 8 new positions
+ * q        [B, Hq, R, D]   contiguous, dtype f16/bf16, D = 64 or 128; R = K+1 new positions
+ *                          (R <= 32 for D = 128, R <= 64 for D = 64; query heads sharing a KV head are
+ *                          processed together while (Hq/Hkv) * R fits the accumulator budget, else in
+ *                          head groups that re-read the KV tile from L2)
  * k_arena  [B, Hkv, C, D]  byte strides kv_stride_b, kv_stride_h, row stride D*elt; the R new rows
  *                          are already appended: rows [0, seq_lens[b] + R) are valid
  * v_arena  same layout
@@ -199,8 +210,13 @@ int sd_kv_set_variant(int variant);
  * out      [B, Hq, R, D]   same dtype as q
  * workspace sd_verify_attention_workspace_bytes(...) bytes (split-KV partials), no init needed
  * scale    softmax scale (1/sqrt(D) when <= 0)
- * n_splits 0 = heuristic
+ * n_splits 0 = heuristic (wave-quantised cost model on max_seq_len_host, bounded by the workspace);
+ *          > 1 needs sd_verify_attention_workspace_bytes(..., n_splits) bytes
+ * max_seq_len_host  upper bound of seq_lens known on the host (-1 = derive from kv_stride_h); only the
+ *          split heuristic uses it -- the kernel reads the true lengths from seq_lens
+ * Returns SD_ERR_UNSUPPORTED for dtype f32, D not in {64,128} or R beyond the limits above.
  * Algorithmic traffic: 2 * B * Hkv * (mean len + R) * D * elt bytes of KV read once per launch.
+ * One launch (+ one small merge launch when n_splits > 1).
  */
 size_t sd_verify_attention_workspace_bytes(int B, int Hq, int R, int D, int max_splits);
 int sd_verify_attention(const void* q, const void* k_arena, const void* v_arena,
@@ -208,6 +224,10 @@ int sd_verify_attention(const void* q, const void* k_arena, const void* v_arena,
                         size_t workspace_bytes, int dtype, int B, int Hq, int Hkv, int R, int D,
                         int64_t kv_stride_b, int64_t kv_stride_h, int64_t max_seq_len_host,
                         float scale, int n_splits, void* stream);
+
+/* Tile configuration of the attention kernel (evidence runs): 0 = heuristic, 1 = 16-key tiles x 3
+ * stages (two CTAs per SM at D = 128), 2 = 32-key tiles x 3 (4 at D = 64) stages, 3 = 32-key x 2. */
+int sd_verify_attention_set_tuning(int config);
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,25 @@
 // Library-level entry points: ABI version, error strings, device query.
 #include "sd_common.cuh"
 
+#include <stdlib.h>
+
+namespace sd {
+static int g_pdl = -1;
+int pdl_enabled() {
+    if (g_pdl < 0) {
+        const char* e = getenv("SD_B200_PDL");
+        g_pdl = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_pdl;
+}
+}  // namespace sd
+
 extern "C" {
+
+int sd_set_pdl(int enabled) {
+    sd::g_pdl = enabled ? 1 : 0;
+    return SD_OK;
+}
 
 int sd_abi_version(void) { return SD_ABI_VERSION; }
 

@@ -14,6 +14,32 @@ namespace sd {
 
 constexpr int kWarp = 32;
 
+// ---- programmatic dependent launch (PDL): every kernel of this library is launched with the
+// programmatic-stream-serialization attribute, so its CTAs may become resident while the previous
+// kernel on the stream drains; griddepcontrol.wait blocks until that kernel has completed and its
+// writes are visible, so it must precede the first global access.  Both instructions are no-ops for a
+// kernel launched without the attribute (sd_set_pdl(0), or the previous work not being a kernel).
+SD_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+SD_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+int pdl_enabled();  // sd_api.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- streaming global loads: read-once data must not displace the KV working set in L1 ----
 SD_DEVINL uint4 ldg_stream_v4(const void* p) {
     uint4 r;

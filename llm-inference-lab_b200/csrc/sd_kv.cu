@@ -9,6 +9,8 @@
 // Two variants, selected by measurement (sd_kv_set_variant):
 //   1  "vec":  one thread per 16-byte vector of an offered row, K and V loads both in flight,
 //              ld.global.nc / st.global 128-bit.
+//   3  "column" (default when rows are 16-byte aligned and unmasked): one thread per 16-byte column of
+//              a (layer, b, h), all R rows of K and V in flight before the first store.
 //   2  "bulk": one thread per (layer, K|V, b, h) unit issues ONE cp.async.bulk (TMA 1-D)
 //              global->shared load of the accepted rows and ONE shared->global bulk store of the R
 //              offered slots (accepted rows followed by zeros) -- no per-element instructions.
@@ -17,6 +19,7 @@
 namespace sd {
 
 static int g_kv_variant = 0;
+static int g_kv_rows_in_flight = 0;  // column kernel: rows per load batch (0 = heuristic)
 
 struct KvParams {
     const sd_kv_layer* layers;  // device table, or nullptr -> `single` (passed by value)
@@ -61,9 +64,11 @@ SD_DEVINL int masked_source_row(const uint8_t* mask, int b, int R, int j) {
 // last CTA to retire publishes the new lengths (so seq_lens_out may alias seq_lens)
 SD_DEVINL void retire_and_commit(const KvParams& p) {
     __shared__ int s_last;
+    // The ticket orders every CTA's READS of seq_lens / n_keep (complete once their values have been
+    // consumed, i.e. before this barrier) ahead of the length commit; the row stores themselves need
+    // no fence -- stream order publishes them to the next kernel.
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
         unsigned prev = atomicAdd(reinterpret_cast<unsigned*>(p.ticket), 1u);
         s_last = prev == p.total_ctas - 1u;
     }
@@ -88,6 +93,8 @@ SD_DEVINL void retire_and_commit(const KvParams& p) {
 
 template <typename VecT>
 __global__ void __launch_bounds__(256) kv_append_vec_kernel(const KvParams p) {
+    pdl_wait();
+    pdl_trigger();
     const int layer = blockIdx.y;
     const int vpr = (int)(p.row_bytes / (int64_t)sizeof(VecT));
     const int64_t slots = (int64_t)p.B * p.H * p.R * vpr;
@@ -137,6 +144,63 @@ __global__ void __launch_bounds__(256) kv_append_vec_kernel(const KvParams p) {
     retire_and_commit(p);
 }
 
+// ---- variant 3 "column": one thread owns one 16-byte column of a (layer, b, h) for ALL R offered
+// rows of K and V: up to 2*RB independent 128-bit loads in flight per thread, issued before the first
+// store, and R-times fewer threads than variant 1 (one wave instead of four).
+template <int RB>
+__global__ void __launch_bounds__(256) kv_append_col_kernel(const KvParams p) {
+    pdl_wait();
+    pdl_trigger();
+    const int layer = blockIdx.y;
+    const int vpr = (int)(p.row_bytes >> 4);
+    const int64_t slots = (int64_t)p.B * p.H * vpr;
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < slots) {
+        const int v = (int)(slot % vpr);
+        const int64_t t = slot / vpr;
+        const int h = (int)(t % p.H);
+        const int b = (int)(t / p.H);
+        const sd_kv_layer L = p.layers ? p.layers[layer] : p.single;
+        const int len = (p.seq_lens ? p.seq_lens[b] : 0) + (int)p.base_len;
+        int n = keep_count(p, b);
+        int room = (int)(p.capacity - len);
+        room = room < 0 ? 0 : (room > p.R ? p.R : room);
+        if (n > room) {
+            if (p.overflow) *p.overflow = 1;
+            n = room;
+        }
+        const int nstore = p.zero_rejected ? room : n;
+        const char* sk = reinterpret_cast<const char*>(L.new_k) + (int64_t)b * p.new_stride_b + (int64_t)h * p.new_stride_h + ((int64_t)v << 4);
+        const char* sv = reinterpret_cast<const char*>(L.new_v) + (int64_t)b * p.new_stride_b + (int64_t)h * p.new_stride_h + ((int64_t)v << 4);
+        const int64_t doff = (int64_t)b * p.arena_stride_b + (int64_t)h * p.arena_stride_h + (int64_t)len * p.row_bytes + ((int64_t)v << 4);
+        char* dk = reinterpret_cast<char*>(L.arena_k) + doff;
+        char* dv = reinterpret_cast<char*>(L.arena_v) + doff;
+        for (int j0 = 0; j0 < nstore; j0 += RB) {
+            uint4 kx[RB], vx[RB];
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {
+                const int j = j0 + u;
+                if (j < n) {
+                    kx[u] = ldg_stream_v4(sk + (int64_t)j * p.new_stride_r);
+                    vx[u] = ldg_stream_v4(sv + (int64_t)j * p.new_stride_r);
+                } else {
+                    kx[u] = make_uint4(0u, 0u, 0u, 0u);
+                    vx[u] = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {
+                const int j = j0 + u;
+                if (j < nstore) {
+                    *reinterpret_cast<uint4*>(dk + (int64_t)j * p.row_bytes) = kx[u];
+                    *reinterpret_cast<uint4*>(dv + (int64_t)j * p.row_bytes) = vx[u];
+                }
+            }
+        }
+    }
+    retire_and_commit(p);
+}
+
 // ---- cp.async.bulk (TMA 1-D) variant -------------------------------------------------------------
 SD_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -174,6 +238,8 @@ SD_DEVINL void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
 
 // One thread per unit (layer, K|V, b, h).  Dynamic smem: blockDim.x * R * row_bytes staging bytes.
 __global__ void __launch_bounds__(128) kv_append_bulk_kernel(const KvParams p) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ __align__(128) unsigned char stage[];
     __shared__ __align__(8) uint64_t bar;
     const int64_t units = (int64_t)p.n_layers * 2 * p.B * p.H;
@@ -243,8 +309,12 @@ static bool aligned_to(const KvParams& p, const sd_kv_layer* host_layers, int n_
 extern "C" {
 
 int sd_kv_set_variant(int variant) {
-    if (variant < 0 || variant > 2) return SD_ERR_INVALID_ARG;
+    // variant 3 + 16 * rows_in_flight selects the column kernel's load batch (evidence runs)
+    const int rif = variant >> 4;
+    variant &= 15;
+    if (variant < 0 || variant > 3 || rif < 0 || rif > 6) return SD_ERR_INVALID_ARG;
     sd::g_kv_variant = variant;
+    sd::g_kv_rows_in_flight = rif;
     return SD_OK;
 }
 
@@ -298,9 +368,28 @@ static int kv_append_impl(const sd_kv_layer* layers, const sd_kv_layer* single, 
     // pointer must be aligned to the chosen vector width (16 bytes for torch allocations).
     const bool bulk_ok = !accepted_mask && aligned_to(p, nullptr, 0, 16) && new_stride_r == row_bytes &&
                          (size_t)R * row_bytes * 32 <= 200 * 1024;
+    const bool col_ok = !accepted_mask && aligned_to(p, nullptr, 0, 16);
     int variant = g_kv_variant;
-    if (variant == 0) variant = 1;
+    if (variant == 0) variant = col_ok ? 3 : 1;
     if (variant == 2 && !bulk_ok) variant = 1;
+    if (variant == 3 && !col_ok) variant = 1;
+
+    if (variant == 3) {
+        const int64_t slots = (int64_t)B * H * (row_bytes / 16);
+        const int threads = 256;
+        dim3 grid((unsigned)((slots + threads - 1) / threads), (unsigned)n_layers);
+        p.total_ctas = grid.x * grid.y;
+        int rb = g_kv_rows_in_flight > 0 ? g_kv_rows_in_flight : (R <= 6 ? R : (R + 1) / 2 <= 6 ? (R + 1) / 2 : 6);
+        if (rb > R) rb = R;
+        switch (rb) {
+            case 1: return to_status(launch_kernel(kv_append_col_kernel<1>, grid, dim3(threads), 0, st, p));
+            case 2: return to_status(launch_kernel(kv_append_col_kernel<2>, grid, dim3(threads), 0, st, p));
+            case 3: return to_status(launch_kernel(kv_append_col_kernel<3>, grid, dim3(threads), 0, st, p));
+            case 4: return to_status(launch_kernel(kv_append_col_kernel<4>, grid, dim3(threads), 0, st, p));
+            case 5: return to_status(launch_kernel(kv_append_col_kernel<5>, grid, dim3(threads), 0, st, p));
+            default: return to_status(launch_kernel(kv_append_col_kernel<6>, grid, dim3(threads), 0, st, p));
+        }
+    }
 
     if (variant == 2) {
         const int64_t units = (int64_t)n_layers * 2 * B * H;
@@ -311,8 +400,7 @@ static int kv_append_impl(const sd_kv_layer* layers, const sd_kv_layer* single, 
         p.total_ctas = ctas;
         cudaError_t e = cudaFuncSetAttribute(kv_append_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return to_status(e);
-        kv_append_bulk_kernel<<<ctas, threads, smem, st>>>(p);
-        return to_status(cudaGetLastError());
+        return to_status(launch_kernel(kv_append_bulk_kernel, dim3(ctas), dim3(threads), smem, st, p));
     }
 
     int vec = 16;
@@ -322,12 +410,11 @@ static int kv_append_impl(const sd_kv_layer* layers, const sd_kv_layer* single, 
     dim3 grid((unsigned)((slots + threads - 1) / threads), (unsigned)n_layers);
     p.total_ctas = grid.x * grid.y;
     switch (vec) {
-        case 16: kv_append_vec_kernel<uint4><<<grid, threads, 0, st>>>(p); break;
-        case 8: kv_append_vec_kernel<uint2><<<grid, threads, 0, st>>>(p); break;
-        case 4: kv_append_vec_kernel<uint32_t><<<grid, threads, 0, st>>>(p); break;
-        default: kv_append_vec_kernel<uint16_t><<<grid, threads, 0, st>>>(p); break;
+        case 16: return to_status(launch_kernel(kv_append_vec_kernel<uint4>, grid, dim3(threads), 0, st, p));
+        case 8: return to_status(launch_kernel(kv_append_vec_kernel<uint2>, grid, dim3(threads), 0, st, p));
+        case 4: return to_status(launch_kernel(kv_append_vec_kernel<uint32_t>, grid, dim3(threads), 0, st, p));
+        default: return to_status(launch_kernel(kv_append_vec_kernel<uint16_t>, grid, dim3(threads), 0, st, p));
     }
-    return to_status(cudaGetLastError());
 }
 
 int sd_kv_append(const sd_kv_layer* layers, int n_layers, int B, int H, int R, int64_t row_bytes,

@@ -1,16 +1,23 @@
 // Kernel 1: fused verify (argmax over V for B*(K+1) rows + accepted-prefix + bonus token).
 //
 // Replaces the reference's verify_prefix (src/kernels/reference.py:13-56; Triton incumbent
-// src/kernels/triton/verify.py:13-98, one serial program per sequence) with ONE streaming pass:
+// src/kernels/triton/verify.py:13-98, one serial program per sequence) with ONE streaming pass.
 //
-//   grid  = B * rows * S CTAs; CTA (row, chunk) reduces a contiguous 16-byte-aligned slice of one
-//           logits row with 128-bit ld.global.nc loads, all loads of a thread issued before use
-//   thread: running packed max (max.NaN.{bf16x2,f16x2,f32}) + the index of the FIRST vector at
-//           which its maximum appeared -- ~1 ALU op per element, so the kernel stays HBM-bound
-//   CTA   : REDUX warp reduce of (order_key, min position) -> one partial per (row, chunk)
-//   last CTA of a sequence (ticket counter) merges the S partials of its rows, resolves the exact
-//           element inside the winning vector, and writes accept_len / mask / target ids / bonus /
-//           packed record.  No second launch, no host round trip.
+// Work decomposition.  A logits row is cut into UNITS of blockDim.x 16-byte vectors (one vector per
+// thread).  A CTA reduces a SEGMENT = a run of consecutive units of one row:
+//   variant 1 "persistent" (default): grid = SMs x resident CTAs; the B*rows*units_per_row units are
+//           split into gridDim.x contiguous, equal (+-1 unit) ranges, so every SM streams the same
+//           number of bytes and there is no partial last wave; a range that crosses a row boundary is
+//           processed as two segments.
+//   variant 0 "tiled": one CTA per (row, chunk of VPT units) -- the first version, kept for sweeps.
+// Per segment:
+//   thread: 128-bit ld.global.nc loads, VPT of them issued before first use; running packed max
+//           (max.NaN.{bf16x2,f16x2,f32}) + the index of the FIRST vector at which its maximum
+//           appeared -- ~1 ALU op per element, so the kernel stays HBM-bound
+//   CTA   : REDUX warp reduce of (order_key, min position) -> one partial per (row, segment)
+//   the CTA that retires the last unit of a sequence (ticket counter, counted in units) merges the
+//           partials of its rows, resolves the exact element inside the winning vector, and writes
+//           accept_len / mask / target ids / bonus / packed record.  No second launch, no host trip.
 //
 // Exact torch.argmax semantics (first maximal index; NaN maximal, first NaN; -0 == +0) are kept
 // by (a) canonical-NaN propagating max, (b) folding -0 to +0 once per vector, (c) tie-breaking
@@ -26,6 +33,8 @@ struct VerifyTuning {
     int vpt;
 };
 static VerifyTuning g_tuning = {0, 0};
+static int g_variant = 0;       // 0 tiled (default: measured faster), 1 persistent
+static int g_ctas_per_sm = 0;   // persistent grid = SMs * this (0 = occupancy)
 
 struct VerifyParams {
     const void* logits;
@@ -45,8 +54,12 @@ struct VerifyParams {
     int32_t* part_pos;    // [B*rows*S]
     float* part_m;        // [B*rows*S] (stats)
     float* part_s;        // [B*rows*S] (stats)
-    uint32_t* tickets;    // [B]
-    int B, rows, K, V, S, chunk_vecs;
+    uint32_t* tickets;    // [B], counts retired units of the sequence
+    int B, rows, K, V;
+    int S;                // partial slots reserved per row
+    int upr;              // units per row (unit = blockDim.x vectors)
+    int units_per_chunk;  // tiled variant: units per CTA
+    int U, q, rem;        // persistent variant: U = B*rows*upr units = gridDim.x*q + rem
     int mode;
     float threshold, scale_log2;  // scale_log2 = inv_temperature * log2(e)
     float inv_temperature;
@@ -78,15 +91,24 @@ SD_DEVINL void merge_ms(float& m, float& s, float m2, float s2) {
     s = a + b;
 }
 
+// contiguous partition of U units over G CTAs: CTA c owns [part_start(c), part_start(c+1))
+SD_DEVINL int part_start(const VerifyParams& p, int c) { return c * p.q + (c < p.rem ? c : p.rem); }
+SD_DEVINL int part_owner(const VerifyParams& p, int u) {
+    const int big = p.rem * (p.q + 1);
+    return u < big ? u / (p.q + 1) : p.rem + (u - big) / p.q;
+}
+
+// Reduce units [it0, it1) of logits row `row` (global row index b*rows + j), publish the partial in
+// `slot` of that row, retire `it1 - it0` units of sequence b and, if they were the last ones,
+// finalize the sequence.  `nslots` = partial slots in use per row for tiled launches, 0 = derive
+// them from the persistent partition.  Called by all threads of the CTA (contains barriers).
 template <typename T, int VPT, bool STATS>
-__global__ void __launch_bounds__((VPT >= 8 || STATS) ? 512 : 1024) verify_kernel(const VerifyParams p) {
+SD_DEVINL void process_segment(const VerifyParams& p, const int row, const int it0, const int it1, const int slot,
+                               const int nslots) {
     using P = Packed<T>;
     constexpr int EPV = 16 / (int)sizeof(T);  // elements per 16-byte vector
     const int tid = threadIdx.x;
     const int nthreads = blockDim.x;
-    const int unit = blockIdx.x;
-    const int chunk = unit % p.S;
-    const int row = unit / p.S;
     const int b = row / p.rows;
     const int j = row - b * p.rows;
 
@@ -98,23 +120,18 @@ __global__ void __launch_bounds__((VPT >= 8 || STATS) ? 512 : 1024) verify_kerne
     if (head > V) head = V;
     const int nvec = (V - head) / EPV;
     const int tail0 = head + nvec * EPV;  // first tail element
+    const uint4* vp = reinterpret_cast<const uint4*>(base + head);
 
-    const int v0 = chunk * p.chunk_vecs;
-    int v1 = v0 + p.chunk_vecs;
-    if (v1 > nvec) v1 = nvec;
-    const int n = v1 > v0 ? v1 - v0 : 0;
-    const uint4* vp = reinterpret_cast<const uint4*>(base + head) + v0;
-
-    uint32_t run = P::kNegInf;  // replicated scalar running max (packed)
-    int first_it = tid < n ? tid : 0x7fffffff;  // vector index (within chunk) where `run` first appeared
+    uint32_t run = P::kNegInf;   // replicated scalar running max (packed)
+    int first_it = 0x7fffffff;   // vector index (within the row) where `run` first appeared
     float sm = -INFINITY, ss = 0.f;  // STATS: reference max (log2 domain) and sum
 
-    for (int i0 = 0; i0 < n; i0 += nthreads * VPT) {
+    for (int i0 = it0; i0 < it1; i0 += VPT) {
         uint4 buf[VPT];
 #pragma unroll
         for (int u = 0; u < VPT; ++u) {
-            int idx = i0 + u * nthreads + tid;
-            if (idx < n) {
+            const int idx = (i0 + u) * nthreads + tid;
+            if (i0 + u < it1 && idx < nvec) {
                 buf[u] = ldg_stream_v4(vp + idx);
             } else {
                 buf[u] = make_uint4(P::kNegInf, P::kNegInf, P::kNegInf, P::kNegInf);
@@ -122,19 +139,21 @@ __global__ void __launch_bounds__((VPT >= 8 || STATS) ? 512 : 1024) verify_kerne
         }
 #pragma unroll
         for (int u = 0; u < VPT; ++u) {
-            int idx = i0 + u * nthreads + tid;
+            const int idx = (i0 + u) * nthreads + tid;
+            const bool live = i0 + u < it1 && idx < nvec;
             uint32_t t = P::vmax(P::vmax(buf[u].x, buf[u].y), P::vmax(buf[u].z, buf[u].w));
             t = P::fold(t);
             uint32_t nw = P::vmax(run, t);
-            bool changed = nw != run;
+            // first live vector always claims the position (run == -inf may equal a row of -inf)
+            bool changed = live && (nw != run || first_it == 0x7fffffff);
             if (changed) first_it = idx;
             if constexpr (STATS) {
-                if (idx < n) {
-                    if (changed) {
-                        float mn = P::scalar(nw) * p.scale_log2;
-                        ss = (sm == -INFINITY) ? 0.f : ss * fast_exp2(sm - mn);
-                        sm = mn;
-                    }
+                if (live && nw != run) {
+                    float mn = P::scalar(nw) * p.scale_log2;
+                    ss = (sm == -INFINITY) ? 0.f : ss * fast_exp2(sm - mn);
+                    sm = mn;
+                }
+                if (live && sm != -INFINITY) {  // a thread that has only seen -inf adds nothing
                     const uint32_t w[4] = {buf[u].x, buf[u].y, buf[u].z, buf[u].w};
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -157,11 +176,11 @@ __global__ void __launch_bounds__((VPT >= 8 || STATS) ? 512 : 1024) verify_kerne
 
     Cand c;
     c.key = order_key(P::scalar(run));
-    c.pos = first_it == 0x7fffffff ? 0x7fffffff : head + (v0 + first_it) * EPV;
-    if (n == 0 || first_it == 0x7fffffff) c.key = 0u;  // thread saw nothing
+    c.pos = first_it == 0x7fffffff ? 0x7fffffff : head + first_it * EPV;
+    if (first_it == 0x7fffffff) c.key = 0u;  // thread saw nothing
 
-    // scalar peel elements (head + tail): handled by chunk 0 only, one element per thread
-    if (chunk == 0) {
+    // scalar peel elements (head + tail): handled by the segment that owns unit 0 of the row
+    if (it0 == 0) {
         const int npeel = head + (V - tail0);
         for (int e = tid; e < npeel; e += nthreads) {
             int pos = e < head ? e : tail0 + (e - head);
@@ -217,31 +236,56 @@ __global__ void __launch_bounds__((VPT >= 8 || STATS) ? 512 : 1024) verify_kerne
                 merge_ms(m2, s2, m3, s3);
             }
         }
+        // exact element inside the winning 16-byte vector (or the peel element itself): resolved per
+        // segment (a 16-byte L2 hit, overlapped by the other resident CTAs) so that the sequence
+        // finalizer at the end of the kernel only has to merge partials
+        {
+            const int e = c2.pos + lane;
+            bool hit = false;
+            if (lane < EPV && c2.pos != 0x7fffffff && e < V) hit = order_key(to_float<T>(base[e])) == c2.key;
+            const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+            if (ballot) c2.pos += __ffs(ballot) - 1;
+        }
         if (lane == 0) {
-            const int slot = row * p.S + chunk;
-            p.part_key[slot] = c2.key;
-            p.part_pos[slot] = c2.pos;
+            const int at = row * p.S + slot;
+            p.part_key[at] = c2.key;
+            p.part_pos[at] = c2.pos;
             if constexpr (STATS) {
-                p.part_m[slot] = m2;
-                p.part_s[slot] = s2;
+                p.part_m[at] = m2;
+                p.part_s[at] = s2;
             }
             __threadfence();
-            unsigned prev = atomicAdd(&p.tickets[b], 1u);
-            s_last = (prev == (unsigned)(p.rows * p.S) - 1u);
+            const unsigned add = (unsigned)(it1 - it0);
+            unsigned prev = atomicAdd(&p.tickets[b], add);
+            s_last = (prev + add == (unsigned)(p.rows * p.upr));
         }
     }
     __syncthreads();
     if (!s_last) return;
 
-    // ---- this CTA retired the last slice of sequence b: finalize the sequence ----
+    // ---- this CTA retired the last units of sequence b: finalize the sequence ----
     __threadfence();
     __shared__ int s_tgt[64];
     __shared__ float s_ptok[64];
+    // draft ids of this sequence: issued now, consumed by warp 0 after the row merge (K <= 63)
+    int my_id[2] = {-1, -1};
+    if (wid == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (h * 32 + lane < p.K) my_id[h] = load_id(p.ids, p.id_dtype, (int64_t)b * p.id_stride_b + h * 32 + lane);
+    }
     for (int r = wid; r < p.rows; r += nwarps) {
         const int grow = b * p.rows + r;
+        const T* rb = reinterpret_cast<const T*>(p.logits) + (int64_t)b * p.stride_b + (int64_t)r * p.stride_r;
+        int tok = -1;
+        if constexpr (STATS) {
+            if (r < p.K && p.mode != SD_ACCEPT_CONFIDENCE) tok = load_id(p.ids, p.id_dtype, (int64_t)b * p.id_stride_b + r);
+        }
+        int ns = nslots;
+        if (ns == 0) ns = part_owner(p, (grow + 1) * p.upr - 1) - part_owner(p, grow * p.upr) + 1;
         Cand best{0u, 0x7fffffff};
         float fm = -INFINITY, fs = 0.f;
-        for (int s = lane; s < p.S; s += 32) {
+        for (int s = lane; s < ns; s += 32) {
             // volatile: written by other CTAs in this launch
             uint32_t k = reinterpret_cast<volatile uint32_t*>(p.part_key)[grow * p.S + s];
             int ps = reinterpret_cast<volatile int32_t*>(p.part_pos)[grow * p.S + s];
@@ -252,6 +296,10 @@ __global__ void __launch_bounds__((VPT >= 8 || STATS) ? 512 : 1024) verify_kerne
                 merge_ms(fm, fs, m2, s2);
             }
         }
+        float xtok = 0.f;
+        if constexpr (STATS) {
+            if (tok >= 0 && tok < V) xtok = to_float<T>(rb[tok]);
+        }
         best = warp_best(best);
         if constexpr (STATS) {
 #pragma unroll
@@ -261,13 +309,7 @@ __global__ void __launch_bounds__((VPT >= 8 || STATS) ? 512 : 1024) verify_kerne
                 merge_ms(fm, fs, m2, s2);
             }
         }
-        // exact element inside the winning 16-byte vector (or the peel element itself)
-        const T* rb = reinterpret_cast<const T*>(p.logits) + (int64_t)b * p.stride_b + (int64_t)r * p.stride_r;
-        int e = best.pos + lane;
-        bool hit = false;
-        if (lane < EPV && best.pos != 0x7fffffff && e < V) hit = order_key(to_float<T>(rb[e])) == best.key;
-        unsigned ballot = __ballot_sync(0xffffffffu, hit);
-        int idx = ballot ? best.pos + (__ffs(ballot) - 1) : 0;
+        const int idx = best.pos == 0x7fffffff ? 0 : best.pos;
         if (lane == 0) {
             s_tgt[r] = idx;
             if (p.target_ids) p.target_ids[grow] = idx;
@@ -278,9 +320,8 @@ __global__ void __launch_bounds__((VPT >= 8 || STATS) ? 512 : 1024) verify_kerne
                 if (r < p.K) {
                     if (p.mode == SD_ACCEPT_CONFIDENCE) {
                         pt = 1.0f / fs;
-                    } else {
-                        int tok = load_id(p.ids, p.id_dtype, (int64_t)b * p.id_stride_b + r);
-                        if (tok >= 0 && tok < V) pt = fast_exp2(to_float<T>(rb[tok]) * p.scale_log2 - fm) / fs;
+                    } else if (tok >= 0 && tok < V) {
+                        pt = fast_exp2(xtok * p.scale_log2 - fm) / fs;
                     }
                     if (p.token_prob) p.token_prob[b * p.K + r] = pt;
                 }
@@ -289,28 +330,65 @@ __global__ void __launch_bounds__((VPT >= 8 || STATS) ? 512 : 1024) verify_kerne
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        int nacc = 0;
-        if constexpr (STATS) {
-            if (p.mode == SD_ACCEPT_GREEDY) {
-                while (nacc < p.K && s_tgt[nacc] == load_id(p.ids, p.id_dtype, (int64_t)b * p.id_stride_b + nacc)) ++nacc;
-            } else {
-                while (nacc < p.K && s_ptok[nacc] >= p.threshold) ++nacc;
+    if (wid == 0) {
+        int nacc = p.K;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = h * 32 + lane;
+            bool bad = false;
+            if (k < p.K) {
+                if (STATS && p.mode != SD_ACCEPT_GREEDY) bad = !(s_ptok[k] >= p.threshold);
+                else bad = s_tgt[k] != my_id[h];
             }
-        } else {
-            while (nacc < p.K && s_tgt[nacc] == load_id(p.ids, p.id_dtype, (int64_t)b * p.id_stride_b + nacc)) ++nacc;
+            const unsigned ballot = __ballot_sync(0xffffffffu, bad);
+            if (ballot && nacc == p.K) nacc = h * 32 + __ffs(ballot) - 1;
         }
-        p.accept_len[b] = nacc;
-        if (p.mask)
-            for (int k = 0; k < p.K; ++k) p.mask[b * p.K + k] = (uint8_t)(k < nacc);
-        const int bon = p.rows > p.K ? s_tgt[nacc] : -1;
-        if (p.bonus) p.bonus[b] = bon;
+        for (int k = lane; k < p.K; k += 32) {
+            if (p.mask) p.mask[b * p.K + k] = (uint8_t)(k < nacc);
+        }
         if (p.packed) {
             int32_t* rec = p.packed + (int64_t)b * (p.K + 2);
-            rec[0] = nacc;
-            for (int r = 0; r <= p.K; ++r) rec[1 + r] = r < p.rows ? s_tgt[r] : -1;
+            for (int r = lane; r <= p.K; r += 32) rec[1 + r] = r < p.rows ? s_tgt[r] : -1;
+            if (lane == 0) rec[0] = nacc;
         }
-        p.tickets[b] = 0u;  // self-reset: the workspace is ready for the next launch / graph replay
+        if (lane == 0) {
+            p.accept_len[b] = nacc;
+            if (p.bonus) p.bonus[b] = p.rows > p.K ? s_tgt[nacc] : -1;
+            p.tickets[b] = 0u;  // self-reset: the workspace is ready for the next launch / graph replay
+        }
+    }
+    __syncthreads();  // s_tgt / s_last are reused by the caller's next segment
+}
+
+// variant 0: one CTA per (row, chunk)
+template <typename T, int VPT, bool STATS>
+__global__ void __launch_bounds__((VPT >= 8 || STATS) ? 512 : 1024) verify_kernel(const VerifyParams p) {
+    pdl_wait();
+    pdl_trigger();
+    const int unit = blockIdx.x;
+    const int chunk = unit % p.S;
+    const int row = unit / p.S;
+    const int it0 = chunk * p.units_per_chunk;
+    int it1 = it0 + p.units_per_chunk;
+    if (it1 > p.upr) it1 = p.upr;
+    process_segment<T, VPT, STATS>(p, row, it0, it1, chunk, p.S);
+}
+
+// variant 1: persistent, equal contiguous unit ranges
+template <typename T, int VPT, bool STATS>
+__global__ void __launch_bounds__(512) verify_persist_kernel(const VerifyParams p) {
+    pdl_wait();
+    pdl_trigger();
+    const int c = blockIdx.x;
+    int u = part_start(p, c);
+    const int end = part_start(p, c + 1);
+    while (u < end) {
+        const int row = u / p.upr;
+        const int it0 = u - row * p.upr;
+        int seg_end = (row + 1) * p.upr;
+        if (seg_end > end) seg_end = end;
+        process_segment<T, VPT, STATS>(p, row, it0, it0 + (seg_end - u), c - part_owner(p, row * p.upr), 0);
+        u = seg_end;
     }
 }
 
@@ -352,16 +430,55 @@ static int sm_count() {
 }
 
 template <typename T, bool STATS>
-static cudaError_t launch_t(const VerifyParams& p, int threads, int vpt, cudaStream_t st) {
-    dim3 grid((unsigned)((size_t)p.B * p.rows * p.S));
-    switch (vpt) {
-        case 1: verify_kernel<T, 1, STATS><<<grid, threads, 0, st>>>(p); break;
-        case 2: verify_kernel<T, 2, STATS><<<grid, threads, 0, st>>>(p); break;
-        case 4: verify_kernel<T, 4, STATS><<<grid, threads, 0, st>>>(p); break;
-        case 8: verify_kernel<T, 8, STATS><<<grid, threads, 0, st>>>(p); break;
-        default: verify_kernel<T, 16, STATS><<<grid, threads, 0, st>>>(p); break;
+static cudaError_t launch_t(const VerifyParams& p, int variant, unsigned grid, int threads, int vpt, cudaStream_t st) {
+    if (variant == 1) {
+        switch (vpt) {
+            case 1: return launch_kernel(verify_persist_kernel<T, 1, STATS>, dim3(grid), dim3(threads), 0, st, p);
+            case 2: return launch_kernel(verify_persist_kernel<T, 2, STATS>, dim3(grid), dim3(threads), 0, st, p);
+            case 4: return launch_kernel(verify_persist_kernel<T, 4, STATS>, dim3(grid), dim3(threads), 0, st, p);
+            case 8: return launch_kernel(verify_persist_kernel<T, 8, STATS>, dim3(grid), dim3(threads), 0, st, p);
+            default: return launch_kernel(verify_persist_kernel<T, 16, STATS>, dim3(grid), dim3(threads), 0, st, p);
+        }
     }
-    return cudaGetLastError();
+    switch (vpt) {
+        case 1: return launch_kernel(verify_kernel<T, 1, STATS>, dim3(grid), dim3(threads), 0, st, p);
+        case 2: return launch_kernel(verify_kernel<T, 2, STATS>, dim3(grid), dim3(threads), 0, st, p);
+        case 4: return launch_kernel(verify_kernel<T, 4, STATS>, dim3(grid), dim3(threads), 0, st, p);
+        case 8: return launch_kernel(verify_kernel<T, 8, STATS>, dim3(grid), dim3(threads), 0, st, p);
+        default: return launch_kernel(verify_kernel<T, 16, STATS>, dim3(grid), dim3(threads), 0, st, p);
+    }
+}
+
+// resident CTAs per SM of the persistent kernel for (T, vpt, stats, threads); cached per combination
+template <typename T, bool STATS>
+static int persist_occupancy_t(int vpt, int threads) {
+    int n = 0;
+    cudaError_t e;
+    switch (vpt) {
+        case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, verify_persist_kernel<T, 1, STATS>, threads, 0); break;
+        case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, verify_persist_kernel<T, 2, STATS>, threads, 0); break;
+        case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, verify_persist_kernel<T, 4, STATS>, threads, 0); break;
+        case 8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, verify_persist_kernel<T, 8, STATS>, threads, 0); break;
+        default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, verify_persist_kernel<T, 16, STATS>, threads, 0); break;
+    }
+    if (e != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        n = 1;
+    }
+    return n;
+}
+
+static int persist_occupancy(int logit_dtype, bool stats, int vpt, int threads) {
+    static int cache[3][2][5][33] = {};  // dtype, stats, log2(vpt), threads/32
+    int lv = 0;
+    while ((1 << lv) < vpt) ++lv;
+    int& slot = cache[logit_dtype][stats ? 1 : 0][lv][threads / 32];
+    if (slot == 0) {
+        if (logit_dtype == SD_F32) slot = stats ? persist_occupancy_t<float, true>(vpt, threads) : persist_occupancy_t<float, false>(vpt, threads);
+        else if (logit_dtype == SD_F16) slot = stats ? persist_occupancy_t<__half, true>(vpt, threads) : persist_occupancy_t<__half, false>(vpt, threads);
+        else slot = stats ? persist_occupancy_t<__nv_bfloat16, true>(vpt, threads) : persist_occupancy_t<__nv_bfloat16, false>(vpt, threads);
+    }
+    return slot;
 }
 
 static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t stride_b, int64_t stride_r,
@@ -385,23 +502,21 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
 
     const int epv = 16 / es;
     const int nvec_max = V / epv + 1;
+    const long long total_vec = (long long)B * rows * nvec_max;
+    int variant = g_variant;
     int threads = g_tuning.threads, vpt = g_tuning.vpt;
     if (threads <= 0 || vpt <= 0) {
-        // heuristic: ~2 waves of 256-thread CTAs with 8 vectors (128 B) in flight per thread
         threads = 256;
-        vpt = 8;
-        const long long total_vec = (long long)B * rows * nvec_max;
-        const long long slots = (long long)sm_count() * 8;
-        while (vpt > 1 && total_vec / ((long long)threads * vpt) < slots) vpt >>= 1;
-        if (stats && vpt > 4) vpt = 4;
+        vpt = stats ? 4 : 8;
+        if (variant == 0) {
+            // ~2 waves of 256-thread CTAs with 8 vectors (128 B) in flight per thread
+            const long long slots = (long long)sm_count() * 8;
+            while (vpt > 1 && total_vec / ((long long)threads * vpt) < slots) vpt >>= 1;
+        }
     }
-    int chunk_vecs = threads * vpt;
-    int S = (nvec_max + chunk_vecs - 1) / chunk_vecs;
-    if (S > kMaxChunks) {  // very long rows: loop inside the CTA instead of adding partials
-        S = kMaxChunks;
-        chunk_vecs = (nvec_max + S - 1) / S;
-    }
-    if (S < 1) S = 1;
+    const int upr = (nvec_max + threads - 1) / threads;  // units per row
+    const long long U = (long long)B * rows * upr;
+    if (U > 0x3fffffffLL) return SD_ERR_UNSUPPORTED;
 
     VerifyParams p;
     p.logits = logits;
@@ -428,23 +543,52 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
     p.rows = rows;
     p.K = K;
     p.V = V;
-    p.S = S;
-    p.chunk_vecs = chunk_vecs;
+    p.upr = upr;
+    p.S = kMaxChunks;
+    p.units_per_chunk = 0;
+    p.U = (int)U;
+    p.q = p.rem = 0;
     p.mode = mode;
     p.threshold = threshold;
     p.inv_temperature = inv_temperature;
     p.scale_log2 = inv_temperature * 1.4426950408889634f;
 
+    unsigned grid;
+    if (variant == 1) {
+        int per_sm = persist_occupancy(logit_dtype, stats, vpt, threads);
+        if (g_ctas_per_sm > 0 && g_ctas_per_sm < per_sm) per_sm = g_ctas_per_sm;
+        long long G = (long long)sm_count() * per_sm;
+        // a CTA should own at least vpt units (one full batch of loads), and a row may be shared by
+        // at most kMaxChunks - 2 CTAs (partial slots): q >= upr / (kMaxChunks - 2)
+        const int q_min = (upr + (kMaxChunks - 3)) / (kMaxChunks - 2) > vpt ? (upr + (kMaxChunks - 3)) / (kMaxChunks - 2) : vpt;
+        if (G * q_min > U) G = U / q_min;
+        if (G < 1) G = 1;
+        p.q = (int)(U / G);
+        p.rem = (int)(U % G);
+        grid = (unsigned)G;
+    } else {
+        int upc = vpt;  // units per chunk
+        int S = (upr + upc - 1) / upc;
+        if (S > kMaxChunks) {  // very long rows: loop inside the CTA instead of adding partials
+            S = kMaxChunks;
+            upc = (upr + S - 1) / S;
+            S = (upr + upc - 1) / upc;
+        }
+        p.S = S;
+        p.units_per_chunk = upc;
+        grid = (unsigned)((size_t)B * rows * S);
+    }
+
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     cudaError_t e;
     if (stats) {
-        if (logit_dtype == SD_F32) e = launch_t<float, true>(p, threads, vpt, st);
-        else if (logit_dtype == SD_F16) e = launch_t<__half, true>(p, threads, vpt, st);
-        else e = launch_t<__nv_bfloat16, true>(p, threads, vpt, st);
+        if (logit_dtype == SD_F32) e = launch_t<float, true>(p, variant, grid, threads, vpt, st);
+        else if (logit_dtype == SD_F16) e = launch_t<__half, true>(p, variant, grid, threads, vpt, st);
+        else e = launch_t<__nv_bfloat16, true>(p, variant, grid, threads, vpt, st);
     } else {
-        if (logit_dtype == SD_F32) e = launch_t<float, false>(p, threads, vpt, st);
-        else if (logit_dtype == SD_F16) e = launch_t<__half, false>(p, threads, vpt, st);
-        else e = launch_t<__nv_bfloat16, false>(p, threads, vpt, st);
+        if (logit_dtype == SD_F32) e = launch_t<float, false>(p, variant, grid, threads, vpt, st);
+        else if (logit_dtype == SD_F16) e = launch_t<__half, false>(p, variant, grid, threads, vpt, st);
+        else e = launch_t<__nv_bfloat16, false>(p, variant, grid, threads, vpt, st);
     }
     return to_status(e);
 }
@@ -473,6 +617,13 @@ int sd_verify_set_tuning(int threads, int vectors_per_thread) {
     if (v != 1 && v != 2 && v != 4 && v != 8 && v != 16) return SD_ERR_INVALID_ARG;
     if (threads > 512) return SD_ERR_INVALID_ARG;  // register budget (stats / 8+-vector kernels are built for <= 512)
     sd::g_tuning = {threads, v};
+    return SD_OK;
+}
+
+int sd_verify_set_variant(int variant, int ctas_per_sm) {
+    if (variant < 0 || variant > 1 || ctas_per_sm < 0 || ctas_per_sm > 32) return SD_ERR_INVALID_ARG;
+    sd::g_variant = variant;
+    sd::g_ctas_per_sm = ctas_per_sm;
     return SD_OK;
 }
 

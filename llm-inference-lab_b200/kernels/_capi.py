@@ -30,6 +30,7 @@ _sz = C.c_size_t
 SIGNATURES = {
     "sd_abi_version": (_i, []),
     "sd_error_string": (C.c_char_p, [_i]),
+    "sd_set_pdl": (_i, [_i]),
     "sd_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "sd_verify_workspace_bytes": (_sz, [_i, _i]),
     "sd_verify_workspace_init": (_i, [_vp, _sz, _vp]),
@@ -38,12 +39,14 @@ SIGNATURES = {
     "sd_verify_step": (_i, [_vp, _i, _i64, _i64, _vp, _i, _i64, _i, _f, _f, _vp, _vp, _vp, _vp, _vp,
                             _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp]),
     "sd_verify_set_tuning": (_i, [_i, _i]),
+    "sd_verify_set_variant": (_i, [_i, _i]),
     "sd_kv_append": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp,
                           _i, _vp, _i, _i64, _vp, _vp, _vp]),
     "sd_kv_append_layer": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                                 _vp, _i, _vp, _i, _vp, _vp]),
     "sd_kv_set_variant": (_i, [_i]),
     "sd_verify_attention_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "sd_verify_attention_set_tuning": (_i, [_i]),
     "sd_verify_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i64, _i64,
                                  _i64, _f, _i, _vp]),
 }

@@ -61,6 +61,16 @@ class _Scratch:
             self._ws[key] = ws
         return ws
 
+    def attn_workspace(self, device: torch.device, need: int) -> torch.Tensor:
+        if torch.cuda.is_current_stream_capturing():
+            return torch.empty(need, dtype=torch.uint8, device=device)
+        key = (device.index or 0, _stream_ptr(device), 1)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=device)
+            self._ws[key] = ws
+        return ws
+
     def ticket(self, device: torch.device) -> torch.Tensor:
         if torch.cuda.is_current_stream_capturing():
             return torch.zeros(1, dtype=torch.int32, device=device)
@@ -429,8 +439,8 @@ def verify_attention_cuda(
     lib = _capi.lib()
     es = q.element_size()
     if workspace is None:
-        need = int(lib.sd_verify_attention_workspace_bytes(B, Hq, R, D, 0))
-        workspace = torch.empty(need, dtype=torch.uint8, device=q.device)
+        need = int(lib.sd_verify_attention_workspace_bytes(B, Hq, R, D, n_splits))
+        workspace = _scratch.attn_workspace(q.device, need)
     with torch.cuda.device(q.device):
         rc = lib.sd_verify_attention(
             q.data_ptr(), k_arena.data_ptr(), v_arena.data_ptr(), seq_lens.data_ptr(), out.data_ptr(),
@@ -498,6 +508,18 @@ def _register_torch_ops() -> None:
 
 def set_verify_tuning(threads: int = 0, vectors_per_thread: int = 0) -> None:
     _capi.lib().check(_capi.lib().sd_verify_set_tuning(threads, vectors_per_thread), "sd_verify_set_tuning")
+
+
+def set_verify_variant(variant: int = 1, ctas_per_sm: int = 0) -> None:
+    _capi.lib().check(_capi.lib().sd_verify_set_variant(variant, ctas_per_sm), "sd_verify_set_variant")
+
+
+def set_attention_tuning(config: int = 0) -> None:
+    _capi.lib().check(_capi.lib().sd_verify_attention_set_tuning(config), "sd_verify_attention_set_tuning")
+
+
+def set_pdl(enabled: bool = True) -> None:
+    _capi.lib().check(_capi.lib().sd_set_pdl(int(enabled)), "sd_set_pdl")
 
 
 def set_kv_variant(variant: int = 0) -> None:

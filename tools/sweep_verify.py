@@ -20,6 +20,9 @@ from specdec.cache.kv_arena import KVArena  # noqa: E402
 from specdec.verify_step import VerifyStep  # noqa: E402
 
 
+GROUP = True  # capture all rotating launches into ONE graph (PDL edges between them) vs one graph each
+
+
 def time_graphs(fns, iters, warm=20):
     side = torch.cuda.Stream()
     graphs = []
@@ -27,22 +30,31 @@ def time_graphs(fns, iters, warm=20):
         fn()
     torch.cuda.synchronize()
     with torch.cuda.stream(side):
-        for fn in fns:
+        if GROUP:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=side):
-                fn()
+                for fn in fns:
+                    fn()
             graphs.append(g)
+        else:
+            for fn in fns:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    fn()
+                graphs.append(g)
     torch.cuda.synchronize()
-    for i in range(warm):
+    per = len(fns) if GROUP else 1
+    reps = max(1, iters // per)
+    for i in range(max(2, warm // per)):
         graphs[i % len(graphs)].replay()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for i in range(iters):
+    for i in range(reps):
         graphs[i % len(graphs)].replay()
     b.record()
     torch.cuda.synchronize()
-    return a.elapsed_time(b) / iters * 1e3  # us
+    return a.elapsed_time(b) / (reps * per) * 1e3  # us per launch
 
 
 def main():
@@ -54,8 +66,18 @@ def main():
     ap.add_argument("--nbuf", type=int, default=4)
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--skip-kv", action="store_true")
+    ap.add_argument("--skip-verify", action="store_true")
+    ap.add_argument("--skip-attn", action="store_true")
+    ap.add_argument("--L", type=int, default=1024)
+    ap.add_argument("--pdl", type=int, default=1)
+    ap.add_argument("--single-graphs", action="store_true", help="one graph per launch (no PDL edges)")
+    ap.add_argument("--quick", action="store_true", help="few configurations")
     ap.add_argument("--stats", action="store_true")
     args = ap.parse_args()
+    global GROUP
+    GROUP = not args.single_graphs
+    cuda_ops.set_pdl(bool(args.pdl))
+    print(json.dumps({"pdl": args.pdl, "group_graph": GROUP, "B": args.B, "K": args.K, "V": args.V}), flush=True)
     dev = torch.device("cuda")
     dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
     B, K, V = args.B, args.K, args.V
@@ -68,16 +90,23 @@ def main():
         steps.append(st)
     nbytes = B * (K + 1) * V * steps[0].logits.element_size()
     results = []
-    configs = [(0, 0)] + [(t, v) for t in (128, 256, 512) for v in (1, 2, 4, 8, 16)]
-    for (t, v) in configs:
-        try:
-            cuda_ops.set_verify_tuning(t, v)
-            us = time_graphs([s.run for s in steps], args.iters)
-            results.append({"kernel": "verify", "threads": t, "vpt": v, "us": us, "GBps": nbytes / us / 1e3})
-            print(json.dumps(results[-1]), flush=True)
-        except Exception as e:  # noqa: BLE001
-            print(json.dumps({"kernel": "verify", "threads": t, "vpt": v, "error": str(e)[:200]}), flush=True)
-    cuda_ops.set_verify_tuning(0, 0)
+    if not args.skip_verify:
+        # (variant, ctas_per_sm, threads, vpt): 1 = persistent equal-range grid, 0 = CTA per (row, chunk)
+        configs = [(1, 0, 0, 0), (0, 0, 0, 0)]
+        if not args.quick:
+            configs += [(1, c, t, v) for t in (256, 512) for v in (2, 4) for c in (0, 4) if not (t == 512 and c == 4)]
+            configs += [(0, 0, t, v) for t in (128, 256, 512) for v in (4, 8, 16)]
+        for (var, cps, t, v) in configs:
+            try:
+                cuda_ops.set_verify_variant(var, cps)
+                cuda_ops.set_verify_tuning(t, v)
+                us = time_graphs([s.run for s in steps], args.iters)
+                results.append({"kernel": "verify", "variant": var, "ctas_per_sm": cps, "threads": t, "vpt": v, "us": us,
+                                "GBps": nbytes / us / 1e3})
+                print(json.dumps(results[-1]), flush=True)
+            except Exception as e:  # noqa: BLE001
+                print(json.dumps({"kernel": "verify", "variant": var, "threads": t, "vpt": v, "error": str(e)[:200]}), flush=True)
+        cuda_ops.set_verify_variant(0, 0)
     # torch.argmax on the same buffers: the ATen incumbent (reference.py:37 on CUDA tensors)
     us = time_graphs([lambda s=s: torch.argmax(s.logits, dim=-1) for s in steps], args.iters)
     print(json.dumps({"kernel": "torch.argmax", "us": us, "GBps": nbytes / us / 1e3}), flush=True)
@@ -95,7 +124,7 @@ def main():
         tables = [arena._build_table(k, v) for k, v in stages]
         accept = torch.randint(0, K + 1, (B,), device=dev, dtype=torch.int32)
         mean_keep = float((accept + 1).float().mean())
-        for variant in (1, 2):
+        for variant in ((1, 3) if args.quick else (1, 2, 3, 3 + 16 * 2, 3 + 16 * 3)):
             for zero in (True, False):
                 cuda_ops.set_kv_variant(variant)
                 arena.set_lengths([L] * B)
@@ -111,6 +140,42 @@ def main():
                 print(json.dumps({"kernel": "kv_append", "variant": variant, "zero_rejected": zero, "us": us,
                                   "GBps": nb / us / 1e3, "bytes": nb, "mean_keep": mean_keep}), flush=True)
         cuda_ops.set_kv_variant(0)
+        del arena, stages, tables
+
+    if not args.skip_attn:
+        # one layer of verify attention per launch, rotating over `nl` layers of arena so KV comes from HBM
+        for (name, Hq, Hkv, D) in (("llama3.2-3b", 24, 8, 128), ("llama3.2-1b", 32, 8, 64)):
+            R, L, nl = K + 1, args.L, 6
+            cap = L + R
+            kk = torch.randn(nl, B, Hkv, cap, D, device=dev).to(torch.bfloat16)
+            vv = torch.randn(nl, B, Hkv, cap, D, device=dev).to(torch.bfloat16)
+            q = torch.randn(B, Hq, R, D, device=dev).to(torch.bfloat16)
+            out = torch.empty_like(q)
+            sl = torch.full((B,), L, dtype=torch.int32, device=dev)
+            nb = 2 * B * Hkv * (L + R) * D * 2 + 2 * B * Hq * R * D * 2
+            flops = 4 * B * Hq * R * (L + R) * D
+            ws = torch.empty(int(cuda_ops._capi.lib().sd_verify_attention_workspace_bytes(B, Hq, R, D, 8)), dtype=torch.uint8, device=dev)
+            for config in ((1,) if args.quick else (1, 2, 3)):
+                for ns in ((0,) if args.quick else (0, 1, 2)):
+                    cuda_ops.set_attention_tuning(config)
+                    fns = [lambda l=l: cuda_ops.verify_attention_cuda(q, kk[l], vv[l], sl, max_seq_len=L, n_splits=ns, out=out, workspace=ws)
+                           for l in range(nl)]
+                    try:
+                        us = time_graphs(fns, args.iters)
+                        print(json.dumps({"kernel": "verify_attention", "model": name, "config": config, "n_splits": ns, "us": us,
+                                          "GBps": nb / us / 1e3, "TFLOPs": flops / us / 1e6, "bytes": nb}), flush=True)
+                    except Exception as e:  # noqa: BLE001
+                        print(json.dumps({"kernel": "verify_attention", "model": name, "config": config, "n_splits": ns, "error": str(e)[:200]}), flush=True)
+            cuda_ops.set_attention_tuning(0)
+            # incumbent: torch SDPA with an explicit mask on the same data (one call for all K+1 queries)
+            mask = torch.arange(cap, device=dev)[None, :] <= (L + torch.arange(R, device=dev))[:, None]
+            fns = [lambda l=l: torch.nn.functional.scaled_dot_product_attention(q, kk[l], vv[l], attn_mask=mask, enable_gqa=True) for l in range(nl)]
+            try:
+                us = time_graphs(fns, args.iters)
+                print(json.dumps({"kernel": "torch.sdpa(gqa,mask)", "model": name, "us": us, "GBps": nb / us / 1e3}), flush=True)
+            except Exception as e:  # noqa: BLE001
+                print(json.dumps({"kernel": "torch.sdpa", "model": name, "error": str(e)[:200]}), flush=True)
+            del kk, vv
 
 
 if __name__ == "__main__":
