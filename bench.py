@@ -42,8 +42,8 @@ CFG = dict(B=64, K=4, V=128256, layers=28, Hq=24, Hkv=8, D=128, L=1024, p_match=
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=40)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
@@ -85,7 +85,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -241,7 +241,10 @@ def run_ours(args):
     R = K + 1
     total_steps = args.steps + args.warmup
     e2e_steps = 0 if args.no_e2e else max(3, min(args.steps, 20))
-    capacity = CFG["L"] + R * (2 * total_steps + 2 * NB + e2e_steps + 16)
+    # sequences are re-seated at context_len every RESEAT steps (a 256-byte device copy between graph
+    # replays: "the batch finished, the next one starts"), so the arena stays small for any --steps
+    RESEAT = 25 * NB
+    capacity = CFG["L"] + R * (RESEAT + 4 * NB + 16)
     arena = KVArena(CFG["layers"], B, CFG["Hkv"], CFG["D"], capacity, R, torch.bfloat16, dev)
     arena.set_lengths([CFG["L"]] * B)
 
@@ -293,12 +296,15 @@ def run_ours(args):
         torch.cuda.synchronize()
 
         def run(n):
-            for _ in range(n // NB):
+            for it in range(n // NB):
+                if it % (RESEAT // NB) == 0:
+                    arena.seq_lens.copy_(base_lens, non_blocking=True)
                 group.replay()
             for s in range(n % NB):
                 singles[s].replay()
         return run
 
+    base_lens = torch.full((B,), CFG["L"], dtype=torch.int32, device=dev)
     run_steps = make_runner(one_step)
     arena.set_lengths([CFG["L"]] * B)
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SD_ABI_VERSION 1
+#define SD_ABI_VERSION 2
 
 /* element type of logits / KV / attention tensors */
 enum sd_dtype { SD_F32 = 0, SD_F16 = 1, SD_BF16 = 2 };
@@ -120,9 +120,17 @@ int sd_verify_step(const void* logits, int logit_dtype, int64_t stride_b, int64_
 /* Tuning hook used by tools/ and bench.py sweeps: threads per CTA (128..1024, multiple of 32),
  * 16-byte vectors in flight per thread (1..16), 0 restores the built-in heuristic. */
 int sd_verify_set_tuning(int threads, int vectors_per_thread);
-/* Kernel variant (evidence runs): 1 = persistent grid with equal contiguous unit ranges (default),
- * 0 = one CTA per (row, chunk).  ctas_per_sm caps the persistent grid (0 = occupancy limit). */
+/* Kernel variant: 0 = one CTA per (row, chunk) with register-staged 128-bit loads; 1 = persistent grid
+ * with equal contiguous unit ranges, register-staged; 2 = persistent grid, cp.async.bulk (TMA 1-D)
+ * copies into a shared-memory mbarrier ring consumed by 256 threads; 3 = one CTA per (row, chunk) whose
+ * whole chunk (vectors_per_thread x 4 KB, <= 48 KB) is fetched by a single cp.async.bulk.  ctas_per_sm caps the persistent
+ * grids (0 = occupancy limit for 1, two CTAs per SM for 2); for variant 2 sd_verify_set_tuning's
+ * vectors_per_thread (2 or 4) selects the ring slot size (8 or 16 KB). */
 int sd_verify_set_variant(int variant, int ctas_per_sm);
+/* Evidence runs: per-CTA timestamps of the variant-0 kernel.  device_buffer holds capacity_ctas x 4
+ * uint64 {globaltimer ns at entry, after the streaming scan, at exit, SM id}; NULL switches it off
+ * (the default; the kernel then only tests one pointer). */
+int sd_verify_set_trace(void* device_buffer, size_t capacity_ctas);
 
 /* ------------------------------------------------------------------------------------------
  * Kernel 2: kv_append into a preallocated arena, with rollback of rejected slots.
@@ -162,6 +170,12 @@ typedef struct sd_kv_layer {
  *             max_seq_len_host >= 0; on device, rows that would fall beyond C are dropped and
  *             *overflow_flag (nullable, int32) is set non-zero.
  * ticket      one int32 in device memory, zero before the first launch (the kernel re-zeroes it).
+ * rows_ready_early  non-zero = the caller guarantees that the layer table and the offered rows were
+ *             written at least two kernels before this call on the stream (in the verify step they
+ *             come from the target forward; the kernel just before this one is the fused verify,
+ *             which writes only accept_len).  The kernel then fetches the first rows of K and V
+ *             before griddepcontrol.wait, overlapping its load phase with the tail of the previous
+ *             kernel; all R <= 6 offered rows are read (rejected ones included).  0 = always safe.
  *
  * Algorithmic traffic per launch: n_layers * 2 * B * H * row_bytes * (mean n read + R written
  * when zero_rejected, else mean n written).
@@ -171,7 +185,8 @@ int sd_kv_append(const sd_kv_layer* layers, int n_layers, int B, int H, int R, i
                  int64_t new_stride_b, int64_t new_stride_h, int64_t new_stride_r,
                  const int32_t* seq_lens, int32_t* seq_lens_out, const int32_t* n_keep,
                  int keep_bias, const uint8_t* accepted_mask, int zero_rejected,
-                 int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, void* stream);
+                 int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, int rows_ready_early,
+                 void* stream);
 
 /*
  * Single-layer form with the layer record passed by value and a uniform current length

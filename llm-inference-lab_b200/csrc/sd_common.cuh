@@ -40,6 +40,12 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+SD_DEVINL unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // ---- streaming global loads: read-once data must not displace the KV working set in L1 ----
 SD_DEVINL uint4 ldg_stream_v4(const void* p) {
     uint4 r;
@@ -48,6 +54,11 @@ SD_DEVINL uint4 ldg_stream_v4(const void* p) {
                  : "l"(p));
     return r;
 }
+// Scheduling fence for a batch of loads: placed after the LAST load of a batch (one call per loaded
+// vector), it keeps the compiler from sinking a load next to its first use -- which would serialise
+// load -> use -> load and leave one request in flight per thread instead of the whole batch.
+SD_DEVINL void pin_loaded(uint4& v) { asm volatile("" : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w)); }
+
 SD_DEVINL void stg_stream_v4(void* p, const uint4& v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
                  "r"(v.z), "r"(v.w)

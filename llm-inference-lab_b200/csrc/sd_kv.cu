@@ -35,6 +35,7 @@ struct KvParams {
     int keep_bias;
     const uint8_t* mask;
     int zero_rejected;
+    int early_rows;  // column kernel: fetch the offered rows before griddepcontrol.wait
     int32_t* overflow;
     int32_t* ticket;
     unsigned total_ctas;
@@ -149,18 +150,48 @@ __global__ void __launch_bounds__(256) kv_append_vec_kernel(const KvParams p) {
 // store, and R-times fewer threads than variant 1 (one wave instead of four).
 template <int RB>
 __global__ void __launch_bounds__(256) kv_append_col_kernel(const KvParams p) {
-    pdl_wait();
-    pdl_trigger();
     const int layer = blockIdx.y;
     const int vpr = (int)(p.row_bytes >> 4);
     const int64_t slots = (int64_t)p.B * p.H * vpr;
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot < slots) {
-        const int v = (int)(slot % vpr);
+    const bool active = slot < slots;
+    int v = 0, h = 0, b = 0;
+    sd_kv_layer L{nullptr, nullptr, nullptr, nullptr};
+    const char* sk = nullptr;
+    const char* sv = nullptr;
+    uint4 kx[RB], vx[RB];
+    // early_rows: the offered rows (and the layer table) were produced at least two kernels ago -- in
+    // the verify step they come from the target forward, and the kernel just before this one is the
+    // fused verify, which only writes accept_len -- so the first RB rows are fetched BEFORE
+    // griddepcontrol.wait, while the previous kernel drains.  Only seq_lens / n_keep wait.
+    if (p.early_rows && active) {
+        v = (int)(slot % vpr);
         const int64_t t = slot / vpr;
-        const int h = (int)(t % p.H);
-        const int b = (int)(t / p.H);
-        const sd_kv_layer L = p.layers ? p.layers[layer] : p.single;
+        h = (int)(t % p.H);
+        b = (int)(t / p.H);
+        L = p.layers ? p.layers[layer] : p.single;
+        sk = reinterpret_cast<const char*>(L.new_k) + (int64_t)b * p.new_stride_b + (int64_t)h * p.new_stride_h + ((int64_t)v << 4);
+        sv = reinterpret_cast<const char*>(L.new_v) + (int64_t)b * p.new_stride_b + (int64_t)h * p.new_stride_h + ((int64_t)v << 4);
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            if (u < p.R) {
+                kx[u] = ldg_stream_v4(sk + (int64_t)u * p.new_stride_r);
+                vx[u] = ldg_stream_v4(sv + (int64_t)u * p.new_stride_r);
+            }
+        }
+    }
+    pdl_wait();
+    pdl_trigger();
+    if (active) {
+        if (!p.early_rows) {
+            v = (int)(slot % vpr);
+            const int64_t t = slot / vpr;
+            h = (int)(t % p.H);
+            b = (int)(t / p.H);
+            L = p.layers ? p.layers[layer] : p.single;
+            sk = reinterpret_cast<const char*>(L.new_k) + (int64_t)b * p.new_stride_b + (int64_t)h * p.new_stride_h + ((int64_t)v << 4);
+            sv = reinterpret_cast<const char*>(L.new_v) + (int64_t)b * p.new_stride_b + (int64_t)h * p.new_stride_h + ((int64_t)v << 4);
+        }
         const int len = (p.seq_lens ? p.seq_lens[b] : 0) + (int)p.base_len;
         int n = keep_count(p, b);
         int room = (int)(p.capacity - len);
@@ -170,30 +201,27 @@ __global__ void __launch_bounds__(256) kv_append_col_kernel(const KvParams p) {
             n = room;
         }
         const int nstore = p.zero_rejected ? room : n;
-        const char* sk = reinterpret_cast<const char*>(L.new_k) + (int64_t)b * p.new_stride_b + (int64_t)h * p.new_stride_h + ((int64_t)v << 4);
-        const char* sv = reinterpret_cast<const char*>(L.new_v) + (int64_t)b * p.new_stride_b + (int64_t)h * p.new_stride_h + ((int64_t)v << 4);
         const int64_t doff = (int64_t)b * p.arena_stride_b + (int64_t)h * p.arena_stride_h + (int64_t)len * p.row_bytes + ((int64_t)v << 4);
         char* dk = reinterpret_cast<char*>(L.arena_k) + doff;
         char* dv = reinterpret_cast<char*>(L.arena_v) + doff;
         for (int j0 = 0; j0 < nstore; j0 += RB) {
-            uint4 kx[RB], vx[RB];
+            if (!(p.early_rows && j0 == 0)) {
 #pragma unroll
-            for (int u = 0; u < RB; ++u) {
-                const int j = j0 + u;
-                if (j < n) {
-                    kx[u] = ldg_stream_v4(sk + (int64_t)j * p.new_stride_r);
-                    vx[u] = ldg_stream_v4(sv + (int64_t)j * p.new_stride_r);
-                } else {
-                    kx[u] = make_uint4(0u, 0u, 0u, 0u);
-                    vx[u] = make_uint4(0u, 0u, 0u, 0u);
+                for (int u = 0; u < RB; ++u) {
+                    const int j = j0 + u;
+                    if (j < n) {
+                        kx[u] = ldg_stream_v4(sk + (int64_t)j * p.new_stride_r);
+                        vx[u] = ldg_stream_v4(sv + (int64_t)j * p.new_stride_r);
+                    }
                 }
             }
 #pragma unroll
             for (int u = 0; u < RB; ++u) {
                 const int j = j0 + u;
                 if (j < nstore) {
-                    *reinterpret_cast<uint4*>(dk + (int64_t)j * p.row_bytes) = kx[u];
-                    *reinterpret_cast<uint4*>(dv + (int64_t)j * p.row_bytes) = vx[u];
+                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(dk + (int64_t)j * p.row_bytes) = j < n ? kx[u] : z;
+                    *reinterpret_cast<uint4*>(dv + (int64_t)j * p.row_bytes) = j < n ? vx[u] : z;
                 }
             }
         }
@@ -323,7 +351,7 @@ static int kv_append_impl(const sd_kv_layer* layers, const sd_kv_layer* single, 
                           int64_t arena_stride_h, int64_t new_stride_b, int64_t new_stride_h,
                           int64_t new_stride_r, const int32_t* seq_lens, int32_t* seq_lens_out,
                           const int32_t* n_keep, int keep_bias, const uint8_t* accepted_mask, int zero_rejected,
-                          int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, void* stream) {
+                          int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, int early_rows, void* stream) {
     using namespace sd;
     if (n_layers < 0 || B < 0 || H < 0 || R < 0 || row_bytes <= 0 || capacity < 0) return SD_ERR_INVALID_ARG;
     if (n_layers == 0 || B == 0 || H == 0) return SD_OK;
@@ -354,6 +382,7 @@ static int kv_append_impl(const sd_kv_layer* layers, const sd_kv_layer* single, 
     p.keep_bias = keep_bias;
     p.mask = accepted_mask;
     p.zero_rejected = zero_rejected;
+    p.early_rows = early_rows ? 1 : 0;
     p.overflow = overflow_flag;
     p.ticket = ticket;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -421,11 +450,11 @@ int sd_kv_append(const sd_kv_layer* layers, int n_layers, int B, int H, int R, i
                  int64_t capacity, int64_t arena_stride_b, int64_t arena_stride_h, int64_t new_stride_b,
                  int64_t new_stride_h, int64_t new_stride_r, const int32_t* seq_lens, int32_t* seq_lens_out,
                  const int32_t* n_keep, int keep_bias, const uint8_t* accepted_mask, int zero_rejected,
-                 int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, void* stream) {
+                 int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, int rows_ready_early, void* stream) {
     if (n_layers > 0 && !layers) return SD_ERR_INVALID_ARG;
     return kv_append_impl(layers, nullptr, 0, n_layers, B, H, R, row_bytes, capacity, arena_stride_b, arena_stride_h,
                           new_stride_b, new_stride_h, new_stride_r, seq_lens, seq_lens_out, n_keep, keep_bias,
-                          accepted_mask, zero_rejected, max_seq_len_host, overflow_flag, ticket, stream);
+                          accepted_mask, zero_rejected, max_seq_len_host, overflow_flag, ticket, rows_ready_early, stream);
 }
 
 int sd_kv_append_layer(void* arena_k, void* arena_v, const void* new_k, const void* new_v, int B, int H, int R,
@@ -437,7 +466,7 @@ int sd_kv_append_layer(void* arena_k, void* arena_v, const void* new_k, const vo
     sd_kv_layer one{arena_k, arena_v, new_k, new_v};
     return kv_append_impl(nullptr, &one, base_len, 1, B, H, R, row_bytes, capacity, arena_stride_b, arena_stride_h,
                           new_stride_b, new_stride_h, new_stride_r, nullptr, nullptr, n_keep, keep_bias,
-                          accepted_mask, zero_rejected, base_len, nullptr, ticket, stream);
+                          accepted_mask, zero_rejected, base_len, nullptr, ticket, 0, stream);
 }
 
 }  // extern "C"

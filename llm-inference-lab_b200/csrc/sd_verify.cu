@@ -15,9 +15,13 @@
 //           (max.NaN.{bf16x2,f16x2,f32}) + the index of the FIRST vector at which its maximum
 //           appeared -- ~1 ALU op per element, so the kernel stays HBM-bound
 //   CTA   : REDUX warp reduce of (order_key, min position) -> one partial per (row, segment)
-//   the CTA that retires the last unit of a sequence (ticket counter, counted in units) merges the
-//           partials of its rows, resolves the exact element inside the winning vector, and writes
-//           accept_len / mask / target ids / bonus / packed record.  No second launch, no host trip.
+//   thread: also keeps a copy of the vector that set its maximum, so the exact element is resolved
+//           from registers -- no dependent re-load at the end of a segment
+//   the partial is published with ONE 64-bit store {key, pos} (0 = "not yet"); the CTA that owns the
+//           last unit of a sequence polls the partial slots of its rows (their producers were
+//           dispatched before it and wait on nothing), merges them, writes accept_len / mask / target
+//           ids / bonus / packed record and re-zeroes the slots.  No fence or atomic on the path of an
+//           ordinary CTA, no second launch, no host trip.
 //
 // Exact torch.argmax semantics (first maximal index; NaN maximal, first NaN; -0 == +0) are kept
 // by (a) canonical-NaN propagating max, (b) folding -0 to +0 once per vector, (c) tie-breaking
@@ -34,6 +38,8 @@ struct VerifyTuning {
 };
 static VerifyTuning g_tuning = {0, 0};
 static int g_variant = 0;       // 0 tiled (default: measured faster), 1 persistent
+static unsigned long long* g_trace = nullptr;  // device buffer for per-CTA timestamps (variant 0 only)
+static size_t g_trace_ctas = 0;
 static int g_ctas_per_sm = 0;   // persistent grid = SMs * this (0 = occupancy)
 
 struct VerifyParams {
@@ -50,11 +56,10 @@ struct VerifyParams {
     float* token_prob;
     float* row_max;
     float* row_sumexp;
-    uint32_t* part_key;   // [B*rows*S]
-    int32_t* part_pos;    // [B*rows*S]
-    float* part_m;        // [B*rows*S] (stats)
-    float* part_s;        // [B*rows*S] (stats)
-    uint32_t* tickets;    // [B], counts retired units of the sequence
+    // partial records, [B*rows*S] x 16 bytes: {u64 kp = order key << 32 | position (0 = not yet
+    // published), float m, float s}.  One array of records (not three arrays) so that a workspace
+    // shared by calls of different (B, rows) never shows one call's statistics as another's kp.
+    unsigned long long* part;
     int B, rows, K, V;
     int S;                // partial slots reserved per row
     int upr;              // units per row (unit = blockDim.x vectors)
@@ -63,6 +68,7 @@ struct VerifyParams {
     int mode;
     float threshold, scale_log2;  // scale_log2 = inv_temperature * log2(e)
     float inv_temperature;
+    unsigned long long* trace;  // evidence runs: [grid][4] = {globaltimer at entry, after the scan, at exit, smid}
 };
 
 struct Cand {
@@ -98,92 +104,154 @@ SD_DEVINL int part_owner(const VerifyParams& p, int u) {
     return u < big ? u / (p.q + 1) : p.rem + (u - big) / p.q;
 }
 
-// Reduce units [it0, it1) of logits row `row` (global row index b*rows + j), publish the partial in
-// `slot` of that row, retire `it1 - it0` units of sequence b and, if they were the last ones,
-// finalize the sequence.  `nslots` = partial slots in use per row for tiled launches, 0 = derive
-// them from the persistent partition.  Called by all threads of the CTA (contains barriers).
-template <typename T, int VPT, bool STATS>
-SD_DEVINL void process_segment(const VerifyParams& p, const int row, const int it0, const int it1, const int slot,
-                               const int nslots) {
-    using P = Packed<T>;
-    constexpr int EPV = 16 / (int)sizeof(T);  // elements per 16-byte vector
-    const int tid = threadIdx.x;
-    const int nthreads = blockDim.x;
+// ---- row geometry: 16-byte aligned interior + scalar peel (rows of e.g. V=50257 bf16 start at
+// arbitrary 2-byte offsets) ----
+template <typename T>
+struct RowGeom {
+    const T* base;     // element 0 of the row
+    const uint4* vp;   // first aligned 16-byte vector (element `head`)
+    int head;          // scalar elements before the first vector
+    int nvec;          // whole vectors
+    int tail0;         // first scalar element after the last vector
+};
+
+template <typename T>
+SD_DEVINL RowGeom<T> row_geom(const VerifyParams& p, int row) {
+    constexpr int EPV = 16 / (int)sizeof(T);
     const int b = row / p.rows;
     const int j = row - b * p.rows;
-
-    const T* base = reinterpret_cast<const T*>(p.logits) + (int64_t)b * p.stride_b + (int64_t)j * p.stride_r;
-    const int V = p.V;
-    // peel to 16-byte alignment (rows of e.g. V=50257 bf16 start at arbitrary 2-byte offsets)
-    const int mis = (int)((reinterpret_cast<uintptr_t>(base) & 15u) / sizeof(T));
+    RowGeom<T> g;
+    g.base = reinterpret_cast<const T*>(p.logits) + (int64_t)b * p.stride_b + (int64_t)j * p.stride_r;
+    const int mis = (int)((reinterpret_cast<uintptr_t>(g.base) & 15u) / sizeof(T));
     int head = mis ? (EPV - mis) : 0;
-    if (head > V) head = V;
-    const int nvec = (V - head) / EPV;
-    const int tail0 = head + nvec * EPV;  // first tail element
-    const uint4* vp = reinterpret_cast<const uint4*>(base + head);
+    if (head > p.V) head = p.V;
+    g.head = head;
+    g.nvec = (p.V - head) / EPV;
+    g.tail0 = head + g.nvec * EPV;
+    g.vp = reinterpret_cast<const uint4*>(g.base + head);
+    return g;
+}
 
-    uint32_t run = P::kNegInf;   // replicated scalar running max (packed)
-    int first_it = 0x7fffffff;   // vector index (within the row) where `run` first appeared
-    float sm = -INFINITY, ss = 0.f;  // STATS: reference max (log2 domain) and sum
+// ---- per-thread running state over the vectors of one row segment ----
+template <typename T, bool STATS>
+struct ThreadAcc {
+    uint32_t run;     // replicated scalar running max (packed)
+    int first_it;     // vector index (within the row) where `run` first appeared
+    uint4 bestv;      // that vector (the exact element is resolved from it at the end of the segment)
+    float sm, ss;     // STATS: reference max (log2 domain) and sum of 2^(x - sm)
 
-    for (int i0 = it0; i0 < it1; i0 += VPT) {
-        uint4 buf[VPT];
-#pragma unroll
-        for (int u = 0; u < VPT; ++u) {
-            const int idx = (i0 + u) * nthreads + tid;
-            if (i0 + u < it1 && idx < nvec) {
-                buf[u] = ldg_stream_v4(vp + idx);
-            } else {
-                buf[u] = make_uint4(P::kNegInf, P::kNegInf, P::kNegInf, P::kNegInf);
-            }
+    SD_DEVINL void reset() {
+        run = Packed<T>::kNegInf;
+        first_it = 0x7fffffff;
+        bestv = make_uint4(0u, 0u, 0u, 0u);
+        sm = -INFINITY;
+        ss = 0.f;
+    }
+
+    // fold one 16-byte vector (index `idx` in its row); `live` = the vector exists
+    SD_DEVINL void add(const uint4& v, int idx, bool live, float scale_log2) {
+        using P = Packed<T>;
+        uint32_t t = P::vmax(P::vmax(v.x, v.y), P::vmax(v.z, v.w));
+        t = P::fold(t);
+        const uint32_t nw = P::vmax(run, t);
+        // first live vector always claims the position (run == -inf may equal a row of -inf)
+        if (live && (nw != run || first_it == 0x7fffffff)) {
+            first_it = idx;
+            bestv = v;
         }
+        if constexpr (STATS) {
+            if (live && nw != run) {
+                float mn = P::scalar(nw) * scale_log2;
+                ss = (sm == -INFINITY) ? 0.f : ss * fast_exp2(sm - mn);
+                sm = mn;
+            }
+            if (live && sm != -INFINITY) {  // a thread that has only seen -inf adds nothing
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int u = 0; u < VPT; ++u) {
-            const int idx = (i0 + u) * nthreads + tid;
-            const bool live = i0 + u < it1 && idx < nvec;
-            uint32_t t = P::vmax(P::vmax(buf[u].x, buf[u].y), P::vmax(buf[u].z, buf[u].w));
-            t = P::fold(t);
-            uint32_t nw = P::vmax(run, t);
-            // first live vector always claims the position (run == -inf may equal a row of -inf)
-            bool changed = live && (nw != run || first_it == 0x7fffffff);
-            if (changed) first_it = idx;
-            if constexpr (STATS) {
-                if (live && nw != run) {
-                    float mn = P::scalar(nw) * p.scale_log2;
-                    ss = (sm == -INFINITY) ? 0.f : ss * fast_exp2(sm - mn);
-                    sm = mn;
-                }
-                if (live && sm != -INFINITY) {  // a thread that has only seen -inf adds nothing
-                    const uint32_t w[4] = {buf[u].x, buf[u].y, buf[u].z, buf[u].w};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if constexpr (sizeof(T) == 4) {
-                            ss += fast_exp2(fmaf(__uint_as_float(w[q]), p.scale_log2, -sm));
-                        } else if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-                            ss += fast_exp2(fmaf(__uint_as_float(w[q] << 16), p.scale_log2, -sm));
-                            ss += fast_exp2(fmaf(__uint_as_float(w[q] & 0xffff0000u), p.scale_log2, -sm));
-                        } else {
-                            float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
-                            ss += fast_exp2(fmaf(f.x, p.scale_log2, -sm));
-                            ss += fast_exp2(fmaf(f.y, p.scale_log2, -sm));
-                        }
+                for (int q = 0; q < 4; ++q) {
+                    if constexpr (sizeof(T) == 4) {
+                        ss += fast_exp2(fmaf(__uint_as_float(w[q]), scale_log2, -sm));
+                    } else if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                        ss += fast_exp2(fmaf(__uint_as_float(w[q] << 16), scale_log2, -sm));
+                        ss += fast_exp2(fmaf(__uint_as_float(w[q] & 0xffff0000u), scale_log2, -sm));
+                    } else {
+                        float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+                        ss += fast_exp2(fmaf(f.x, scale_log2, -sm));
+                        ss += fast_exp2(fmaf(f.y, scale_log2, -sm));
                     }
                 }
             }
-            run = nw;
+        }
+        run = nw;
+    }
+};
+
+// first maximal element of one 16-byte vector whose first element has row index `pos0`
+template <typename T>
+SD_DEVINL Cand exact_in_vector(const uint4& v, int pos0) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    Cand c{0u, 0x7fffffff};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if constexpr (sizeof(T) == 4) {
+            c = better(c, Cand{order_key(__uint_as_float(w[q])), pos0 + q});
+        } else if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+            c = better(c, Cand{order_key(__uint_as_float(w[q] << 16)), pos0 + 2 * q});
+            c = better(c, Cand{order_key(__uint_as_float(w[q] & 0xffff0000u)), pos0 + 2 * q + 1});
+        } else {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+            c = better(c, Cand{order_key(f.x), pos0 + 2 * q});
+            c = better(c, Cand{order_key(f.y), pos0 + 2 * q + 1});
         }
     }
+    return c;
+}
 
-    Cand c;
-    c.key = order_key(P::scalar(run));
-    c.pos = first_it == 0x7fffffff ? 0x7fffffff : head + first_it * EPV;
-    if (first_it == 0x7fffffff) c.key = 0u;  // thread saw nothing
+SD_DEVINL unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+SD_DEVINL void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// CTA-wide barrier over the `nthreads` reducing threads: __syncthreads, or named barrier 1 when the
+// CTA also holds a producer warp that must not take part
+template <bool NAMED>
+SD_DEVINL void cta_sync(int nthreads) {
+    if constexpr (NAMED) {
+        asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+    } else {
+        __syncthreads();
+    }
+}
+
+// Close the segment [it0, it1) of logits row `row` (global row index b*rows + j): fold the scalar peel
+// elements, reduce the CTA and publish the partial in `slot` of that row.  Returns true when the
+// segment holds the last unit of its sequence: that CTA must call finalize_sequence(b) -- right away
+// in the tiled variants (one segment per CTA), after its whole range in the persistent ones (a CTA
+// that stopped to wait in the middle of its range would stall the CTAs waiting for ITS later
+// partials).  Called by all `nthreads` reducing threads (tid in [0, nthreads)); contains barriers.
+template <typename T, bool STATS, bool NAMED>
+SD_DEVINL bool publish_segment(const VerifyParams& p, const RowGeom<T>& g, ThreadAcc<T, STATS>& acc, const int row,
+                               const int it0, const int it1, const int slot, const int tid, const int nthreads) {
+    using P = Packed<T>;
+    constexpr int EPV = 16 / (int)sizeof(T);
+    const int b = row / p.rows;
+    const int V = p.V;
+    const T* base = g.base;
+    float sm = acc.sm, ss = acc.ss;
+
+    // exact (key, position) of this thread's maximum, from the vector it kept
+    Cand c{0u, 0x7fffffff};  // nothing seen
+    if (acc.first_it != 0x7fffffff) c = exact_in_vector<T>(acc.bestv, g.head + acc.first_it * EPV);
 
     // scalar peel elements (head + tail): handled by the segment that owns unit 0 of the row
     if (it0 == 0) {
-        const int npeel = head + (V - tail0);
+        const int npeel = g.head + (V - g.tail0);
         for (int e = tid; e < npeel; e += nthreads) {
-            int pos = e < head ? e : tail0 + (e - head);
+            int pos = e < g.head ? e : g.tail0 + (e - g.head);
             float x = to_float<T>(base[pos]);
             Cand c2{order_key(x), pos};
             c = better(c, c2);
@@ -199,7 +267,6 @@ SD_DEVINL void process_segment(const VerifyParams& p, const int row, const int i
     __shared__ int s_pos[32];
     __shared__ float s_m[32];
     __shared__ float s_s[32];
-    __shared__ int s_last;
     const int lane = tid & 31, wid = tid >> 5, nwarps = nthreads >> 5;
 
     c = warp_best(c);
@@ -219,7 +286,7 @@ SD_DEVINL void process_segment(const VerifyParams& p, const int row, const int i
             s_s[wid] = ss;
         }
     }
-    __syncthreads();
+    cta_sync<NAMED>(nthreads);
     if (wid == 0) {
         Cand c2 = lane < nwarps ? Cand{s_key[lane], s_pos[lane]} : Cand{0u, 0x7fffffff};
         c2 = warp_best(c2);
@@ -236,38 +303,30 @@ SD_DEVINL void process_segment(const VerifyParams& p, const int row, const int i
                 merge_ms(m2, s2, m3, s3);
             }
         }
-        // exact element inside the winning 16-byte vector (or the peel element itself): resolved per
-        // segment (a 16-byte L2 hit, overlapped by the other resident CTAs) so that the sequence
-        // finalizer at the end of the kernel only has to merge partials
-        {
-            const int e = c2.pos + lane;
-            bool hit = false;
-            if (lane < EPV && c2.pos != 0x7fffffff && e < V) hit = order_key(to_float<T>(base[e])) == c2.key;
-            const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-            if (ballot) c2.pos += __ffs(ballot) - 1;
-        }
         if (lane == 0) {
-            const int at = row * p.S + slot;
-            p.part_key[at] = c2.key;
-            p.part_pos[at] = c2.pos;
+            unsigned long long* rec = p.part + 2 * ((size_t)row * p.S + slot);
             if constexpr (STATS) {
-                p.part_m[at] = m2;
-                p.part_s[at] = s2;
+                *reinterpret_cast<float2*>(rec + 1) = make_float2(m2, s2);
+                __threadfence();  // the statistics must be visible before the slot reads "published"
             }
-            __threadfence();
-            const unsigned add = (unsigned)(it1 - it0);
-            unsigned prev = atomicAdd(&p.tickets[b], add);
-            s_last = (prev + add == (unsigned)(p.rows * p.upr));
+            // {key, pos} is never 0: an empty candidate carries pos 0x7fffffff
+            st_volatile_u64(rec, ((unsigned long long)c2.key << 32) | (unsigned)c2.pos);
         }
     }
-    __syncthreads();
-    if (!s_last) return;
+    cta_sync<NAMED>(nthreads);  // s_key .. s_s are rewritten by the caller's next segment
+    return (row - b * p.rows == p.rows - 1) && (it1 == p.upr);
+}
 
-    // ---- this CTA retired the last units of sequence b: finalize the sequence ----
-    __threadfence();
+// Finalize sequence b: wait for the partials of its rows, merge them, evaluate the acceptance rule,
+// write the outputs and re-arm the slots.  `nslots` = partial slots in use per row for tiled launches,
+// 0 = derive them from the persistent partition.  Called by all `nthreads` reducing threads.
+template <typename T, bool STATS, bool NAMED>
+SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int nslots, const int tid, const int nthreads) {
+    const int V = p.V;
+    const int lane = tid & 31, wid = tid >> 5, nwarps = nthreads >> 5;
     __shared__ int s_tgt[64];
     __shared__ float s_ptok[64];
-    // draft ids of this sequence: issued now, consumed by warp 0 after the row merge (K <= 63)
+    // draft ids of this sequence: issued now, consumed by warp 0 after the row merge (K <= 64)
     int my_id[2] = {-1, -1};
     if (wid == 0) {
 #pragma unroll
@@ -283,19 +342,32 @@ SD_DEVINL void process_segment(const VerifyParams& p, const int row, const int i
         }
         int ns = nslots;
         if (ns == 0) ns = part_owner(p, (grow + 1) * p.upr - 1) - part_owner(p, grow * p.upr) + 1;
+        unsigned long long* slots = p.part + 2 * ((size_t)grow * p.S);  // record i at slots[2 * i]
+        // ns <= kMaxChunks = 64: two slots per lane.  Their producers were dispatched before this CTA
+        // (lower block index) and wait on nothing, so the poll terminates.
+        unsigned long long v0 = 1ull, v1 = 1ull;
+        for (;;) {
+            if (lane < ns) v0 = ld_volatile_u64(slots + 2 * lane);
+            if (lane + 32 < ns) v1 = ld_volatile_u64(slots + 2 * (lane + 32));
+            if (__all_sync(0xffffffffu, v0 != 0ull && v1 != 0ull)) break;
+            __nanosleep(40);
+        }
         Cand best{0u, 0x7fffffff};
+        if (lane < ns) best = better(best, Cand{(uint32_t)(v0 >> 32), (int)(uint32_t)v0});
+        if (lane + 32 < ns) best = better(best, Cand{(uint32_t)(v1 >> 32), (int)(uint32_t)v1});
         float fm = -INFINITY, fs = 0.f;
-        for (int s = lane; s < ns; s += 32) {
-            // volatile: written by other CTAs in this launch
-            uint32_t k = reinterpret_cast<volatile uint32_t*>(p.part_key)[grow * p.S + s];
-            int ps = reinterpret_cast<volatile int32_t*>(p.part_pos)[grow * p.S + s];
-            best = better(best, Cand{k, ps});
-            if constexpr (STATS) {
-                float m2 = reinterpret_cast<volatile float*>(p.part_m)[grow * p.S + s];
-                float s2 = reinterpret_cast<volatile float*>(p.part_s)[grow * p.S + s];
+        if constexpr (STATS) {
+            __threadfence();
+            for (int sidx = lane; sidx < ns; sidx += 32) {
+                const volatile float* ms = reinterpret_cast<const volatile float*>(slots + 2 * sidx + 1);
+                float m2 = ms[0];
+                float s2 = ms[1];
                 merge_ms(fm, fs, m2, s2);
             }
         }
+        // re-arm the slots for the next launch / graph replay (this CTA is their only reader)
+        if (lane < ns) slots[2 * lane] = 0ull;
+        if (lane + 32 < ns) slots[2 * (lane + 32)] = 0ull;
         float xtok = 0.f;
         if constexpr (STATS) {
             if (tok >= 0 && tok < V) xtok = to_float<T>(rb[tok]);
@@ -329,7 +401,7 @@ SD_DEVINL void process_segment(const VerifyParams& p, const int row, const int i
             }
         }
     }
-    __syncthreads();
+    cta_sync<NAMED>(nthreads);
     if (wid == 0) {
         int nacc = p.K;
 #pragma unroll
@@ -354,29 +426,72 @@ SD_DEVINL void process_segment(const VerifyParams& p, const int row, const int i
         if (lane == 0) {
             p.accept_len[b] = nacc;
             if (p.bonus) p.bonus[b] = p.rows > p.K ? s_tgt[nacc] : -1;
-            p.tickets[b] = 0u;  // self-reset: the workspace is ready for the next launch / graph replay
         }
     }
-    __syncthreads();  // s_tgt / s_last are reused by the caller's next segment
+    cta_sync<NAMED>(nthreads);  // s_tgt and the reduce scratch are reused by the caller's next segment
+}
+
+// Reduce units [it0, it1) of logits row `row` with register-staged 128-bit loads (VPT in flight per
+// thread) and close the segment.  Called by all threads of the CTA.
+template <typename T, int VPT, bool STATS>
+SD_DEVINL bool process_segment(const VerifyParams& p, const int row, const int it0, const int it1, const int slot) {
+    using P = Packed<T>;
+    const int tid = threadIdx.x;
+    const int nthreads = blockDim.x;
+    const RowGeom<T> g = row_geom<T>(p, row);
+    ThreadAcc<T, STATS> acc;
+    acc.reset();
+    for (int i0 = it0; i0 < it1; i0 += VPT) {
+        uint4 buf[VPT];
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) {
+            const int idx = (i0 + u) * nthreads + tid;
+            if (i0 + u < it1 && idx < g.nvec) {
+                buf[u] = ldg_stream_v4(g.vp + idx);
+            } else {
+                buf[u] = make_uint4(P::kNegInf, P::kNegInf, P::kNegInf, P::kNegInf);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) pin_loaded(buf[u]);
+        __syncwarp();  // memory-ordering point: ptxas keeps all VPT loads of the batch ahead of their first use
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) {
+            const int idx = (i0 + u) * nthreads + tid;
+            acc.add(buf[u], idx, i0 + u < it1 && idx < g.nvec, p.scale_log2);
+        }
+    }
+    if (p.trace && tid == 0) p.trace[(size_t)blockIdx.x * 4 + 1] = global_timer_ns();
+    return publish_segment<T, STATS, false>(p, g, acc, row, it0, it1, slot, tid, nthreads);
 }
 
 // variant 0: one CTA per (row, chunk)
 template <typename T, int VPT, bool STATS>
-__global__ void __launch_bounds__((VPT >= 8 || STATS) ? 512 : 1024) verify_kernel(const VerifyParams p) {
+// launch bounds: (512, 3) makes ptxas settle on ~40 registers and keep all VPT loads of a batch in
+// flight before the first use; with a laxer or tighter bound it serialises load -> use (SASS checked)
+__global__ void __launch_bounds__(512, STATS ? 2 : 3) verify_kernel(const VerifyParams p) {
     pdl_wait();
     pdl_trigger();
     const int unit = blockIdx.x;
+    if (p.trace && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.trace[(size_t)unit * 4 + 0] = global_timer_ns();
+        p.trace[(size_t)unit * 4 + 3] = smid;
+    }
     const int chunk = unit % p.S;
     const int row = unit / p.S;
     const int it0 = chunk * p.units_per_chunk;
     int it1 = it0 + p.units_per_chunk;
     if (it1 > p.upr) it1 = p.upr;
-    process_segment<T, VPT, STATS>(p, row, it0, it1, chunk, p.S);
+    if (process_segment<T, VPT, STATS>(p, row, it0, it1, chunk))
+        finalize_sequence<T, STATS, false>(p, row / p.rows, p.S, threadIdx.x, blockDim.x);
+    if (p.trace && threadIdx.x == 0) p.trace[(size_t)unit * 4 + 2] = global_timer_ns();
 }
 
 // variant 1: persistent, equal contiguous unit ranges
 template <typename T, int VPT, bool STATS>
-__global__ void __launch_bounds__(512) verify_persist_kernel(const VerifyParams p) {
+__global__ void __launch_bounds__(512, STATS ? 2 : 3) verify_persist_kernel(const VerifyParams p) {
     pdl_wait();
     pdl_trigger();
     const int c = blockIdx.x;
@@ -387,33 +502,207 @@ __global__ void __launch_bounds__(512) verify_persist_kernel(const VerifyParams 
         const int it0 = u - row * p.upr;
         int seg_end = (row + 1) * p.upr;
         if (seg_end > end) seg_end = end;
-        process_segment<T, VPT, STATS>(p, row, it0, it0 + (seg_end - u), c - part_owner(p, row * p.upr), 0);
+        process_segment<T, VPT, STATS>(p, row, it0, it0 + (seg_end - u), c - part_owner(p, row * p.upr));
         u = seg_end;
     }
+    // sequences whose last unit lies in this CTA's range (all partials of this CTA are published)
+    const int su = p.rows * p.upr;
+    for (int b = part_start(p, c) / su; b <= end / su - 1; ++b)
+        finalize_sequence<T, STATS, false>(p, b, 0, threadIdx.x, blockDim.x);
+}
+
+// ---- variant 2: persistent + TMA bulk staging -----------------------------------------------------
+// One producer warp keeps `stages` cp.async.bulk (TMA 1-D) copies of UNIT = 256*VPU vectors in flight
+// into a shared-memory ring (mbarrier full/empty pairs); 256 consumer threads fold each landed unit
+// from shared memory.  Loads stay in flight while the consumers run a segment epilogue, and no
+// registers are tied up by outstanding loads.
+constexpr int kTmaConsumers = 256;
+constexpr int kTmaMaxStages = 32;
+
+SD_DEVINL uint32_t smem_u32v(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+SD_DEVINL void vbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32v(bar)), "r"(count) : "memory");
+}
+SD_DEVINL void vbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32v(bar)) : "memory");
+}
+SD_DEVINL void vbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32v(bar)), "r"(bytes) : "memory");
+}
+SD_DEVINL void vbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32v(bar)), "r"(parity)
+            : "memory");
+    }
+}
+SD_DEVINL void vbulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32v(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32v(bar))
+                 : "memory");
+}
+
+template <typename T, int VPU, bool STATS>
+__global__ void __launch_bounds__(kTmaConsumers + 32) verify_tma_kernel(const VerifyParams p, const int stages) {
+    using P = Packed<T>;
+    constexpr int UV = kTmaConsumers * VPU;  // vectors per unit
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ __align__(8) uint64_t full_bar[kTmaMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kTmaMaxStages];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            vbar_init(&full_bar[s], 1);
+            vbar_init(&empty_bar[s], kTmaConsumers / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_wait();
+    pdl_trigger();
+
+    const int c = blockIdx.x;
+    const int u_begin = part_start(p, c);
+    const int u_end = part_start(p, c + 1);
+
+    if (tid >= kTmaConsumers) {  // ---- producer warp: one elected lane issues the bulk copies ----
+        if (tid == kTmaConsumers) {
+            int s = 0;
+            unsigned ph = 0;
+            int row = -1;
+            RowGeom<T> g;
+            for (int u = u_begin; u < u_end; ++u) {
+                const int r = u / p.upr;
+                if (r != row) {
+                    row = r;
+                    g = row_geom<T>(p, row);
+                }
+                const int v0 = (u - row * p.upr) * UV;
+                int nv = g.nvec - v0;
+                nv = nv < 0 ? 0 : (nv > UV ? UV : nv);
+                vbar_wait(&empty_bar[s], ph ^ 1u);  // slot free (first lap passes immediately)
+                if (nv > 0) {
+                    vbar_arrive_expect_tx(&full_bar[s], (unsigned)nv * 16u);
+                    vbulk_g2s(ring + (size_t)s * (UV * 16), g.vp + v0, (unsigned)nv * 16u, &full_bar[s]);
+                } else {
+                    vbar_arrive(&full_bar[s]);
+                }
+                if (++s == stages) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers ----
+    const int lane = tid & 31;
+    int s = 0;
+    unsigned ph = 0;
+    int u = u_begin;
+    while (u < u_end) {
+        const int row = u / p.upr;
+        const int it0 = u - row * p.upr;
+        int seg_end = (row + 1) * p.upr;
+        if (seg_end > u_end) seg_end = u_end;
+        const RowGeom<T> g = row_geom<T>(p, row);
+        ThreadAcc<T, STATS> acc;
+        acc.reset();
+        for (int uu = u; uu < seg_end; ++uu) {
+            const int v0 = (uu - row * p.upr) * UV;
+            vbar_wait(&full_bar[s], ph);
+            const uint4* src = reinterpret_cast<const uint4*>(ring + (size_t)s * (UV * 16));
+            uint4 buf[VPU];
+#pragma unroll
+            for (int k = 0; k < VPU; ++k) {
+                const int idx = v0 + k * kTmaConsumers + tid;
+                buf[k] = idx < g.nvec ? src[k * kTmaConsumers + tid] : make_uint4(P::kNegInf, P::kNegInf, P::kNegInf, P::kNegInf);
+            }
+#pragma unroll
+            for (int k = 0; k < VPU; ++k) pin_loaded(buf[k]);
+            __syncwarp();
+            if (lane == 0) vbar_arrive(&empty_bar[s]);  // this warp's reads of the slot are done
+#pragma unroll
+            for (int k = 0; k < VPU; ++k) {
+                const int idx = v0 + k * kTmaConsumers + tid;
+                acc.add(buf[k], idx, idx < g.nvec, p.scale_log2);
+            }
+            if (++s == stages) {
+                s = 0;
+                ph ^= 1u;
+            }
+        }
+        publish_segment<T, STATS, true>(p, g, acc, row, it0, it0 + (seg_end - u), c - part_owner(p, row * p.upr), tid,
+                                        kTmaConsumers);
+        u = seg_end;
+    }
+    const int su = p.rows * p.upr;
+    for (int b = u_begin / su; b <= u_end / su - 1; ++b) finalize_sequence<T, STATS, true>(p, b, 0, tid, kTmaConsumers);
+}
+
+// ---- variant 3: one CTA per (row, chunk), the whole chunk fetched by ONE cp.async.bulk -------------
+// Thread 0 issues a single TMA 1-D copy of the chunk (upc * blockDim.x vectors, up to ~48 KB) into
+// shared memory and every thread waits on the mbarrier; the chunk is then folded from shared memory.
+// All of a CTA's bytes are in flight after one instruction, independent of register allocation, and
+// several CTAs per SM overlap each other's wait / fold / publish phases.
+template <typename T, bool STATS>
+__global__ void __launch_bounds__(256) verify_bulk_kernel(const VerifyParams p) {
+    extern __shared__ __align__(128) unsigned char stage[];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    if (tid == 0) {
+        vbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_wait();
+    pdl_trigger();
+    const int unit = blockIdx.x;
+    const int chunk = unit % p.S;
+    const int row = unit / p.S;
+    const int it0 = chunk * p.units_per_chunk;
+    int it1 = it0 + p.units_per_chunk;
+    if (it1 > p.upr) it1 = p.upr;
+    const RowGeom<T> g = row_geom<T>(p, row);
+    const int v0 = it0 * nthreads;
+    int nv = g.nvec - v0;
+    const int cap = (it1 - it0) * nthreads;
+    nv = nv < 0 ? 0 : (nv > cap ? cap : nv);
+    if (tid == 0) {
+        if (nv > 0) {
+            vbar_arrive_expect_tx(&bar, (unsigned)nv * 16u);
+            vbulk_g2s(stage, g.vp + v0, (unsigned)nv * 16u, &bar);
+        } else {
+            vbar_arrive(&bar);
+        }
+    }
+    vbar_wait(&bar, 0u);
+    ThreadAcc<T, STATS> acc;
+    acc.reset();
+    const uint4* src = reinterpret_cast<const uint4*>(stage);
+#pragma unroll 4
+    for (int k = tid; k < nv; k += nthreads) acc.add(src[k], v0 + k, true, p.scale_log2);
+    if (publish_segment<T, STATS, false>(p, g, acc, row, it0, it1, chunk, tid, nthreads))
+        finalize_sequence<T, STATS, false>(p, row / p.rows, p.S, tid, nthreads);
 }
 
 // ------------------------------------------------------------------------------------------ host
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct WorkspaceLayout {
-    size_t key, pos, m, s, tickets, total;
+    size_t total;
 };
 
 static WorkspaceLayout layout(int B, int rows) {
     WorkspaceLayout w;
-    size_t n = (size_t)B * rows * kMaxChunks;
-    size_t off = 0;
-    w.tickets = off;
-    off = align_up(off + (size_t)B * 4, 256);
-    w.key = off;
-    off = align_up(off + n * 4, 256);
-    w.pos = off;
-    off = align_up(off + n * 4, 256);
-    w.m = off;
-    off = align_up(off + n * 4, 256);
-    w.s = off;
-    off = align_up(off + n * 4, 256);
-    w.total = off;
+    w.total = align_up((size_t)B * rows * kMaxChunks * 16, 256);
     return w;
 }
 
@@ -444,9 +733,32 @@ static cudaError_t launch_t(const VerifyParams& p, int variant, unsigned grid, i
         case 1: return launch_kernel(verify_kernel<T, 1, STATS>, dim3(grid), dim3(threads), 0, st, p);
         case 2: return launch_kernel(verify_kernel<T, 2, STATS>, dim3(grid), dim3(threads), 0, st, p);
         case 4: return launch_kernel(verify_kernel<T, 4, STATS>, dim3(grid), dim3(threads), 0, st, p);
+        case 5: return launch_kernel(verify_kernel<T, 5, STATS>, dim3(grid), dim3(threads), 0, st, p);
+        case 6: return launch_kernel(verify_kernel<T, 6, STATS>, dim3(grid), dim3(threads), 0, st, p);
+        case 7: return launch_kernel(verify_kernel<T, 7, STATS>, dim3(grid), dim3(threads), 0, st, p);
         case 8: return launch_kernel(verify_kernel<T, 8, STATS>, dim3(grid), dim3(threads), 0, st, p);
         default: return launch_kernel(verify_kernel<T, 16, STATS>, dim3(grid), dim3(threads), 0, st, p);
     }
+}
+
+template <typename T, bool STATS>
+static cudaError_t launch_tma_t(const VerifyParams& p, unsigned grid, int vpu, int stages, size_t smem, cudaStream_t st) {
+    cudaError_t e;
+    if (vpu == 2) {
+        e = cudaFuncSetAttribute(verify_tma_kernel<T, 2, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        return launch_kernel(verify_tma_kernel<T, 2, STATS>, dim3(grid), dim3(kTmaConsumers + 32), smem, st, p, stages);
+    }
+    e = cudaFuncSetAttribute(verify_tma_kernel<T, 4, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return launch_kernel(verify_tma_kernel<T, 4, STATS>, dim3(grid), dim3(kTmaConsumers + 32), smem, st, p, stages);
+}
+
+template <typename T, bool STATS>
+static cudaError_t launch_bulk_t(const VerifyParams& p, unsigned grid, int threads, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(verify_bulk_kernel<T, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return launch_kernel(verify_bulk_kernel<T, STATS>, dim3(grid), dim3(threads), smem, st, p);
 }
 
 // resident CTAs per SM of the persistent kernel for (T, vpt, stats, threads); cached per combination
@@ -496,7 +808,7 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
         return SD_ERR_INVALID_ARG;
     if (mode < SD_ACCEPT_GREEDY || mode > SD_ACCEPT_CONFIDENCE) return SD_ERR_INVALID_ARG;
     const int es = elt_size(logit_dtype);
-    if (reinterpret_cast<uintptr_t>(logits) % es) return SD_ERR_ALIGNMENT;
+    if (reinterpret_cast<uintptr_t>(logits) % es || reinterpret_cast<uintptr_t>(workspace) % 8) return SD_ERR_ALIGNMENT;
     WorkspaceLayout w = layout(B, rows);
     if (!workspace || workspace_bytes < w.total) return SD_ERR_WORKSPACE;
 
@@ -514,7 +826,19 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
             while (vpt > 1 && total_vec / ((long long)threads * vpt) < slots) vpt >>= 1;
         }
     }
-    const int upr = (nvec_max + threads - 1) / threads;  // units per row
+    if (variant == 1 && vpt != 1 && vpt != 2 && vpt != 4 && vpt != 8) vpt = vpt > 8 ? 16 : (vpt > 4 ? 8 : 4);
+    if (variant == 0 && vpt > 8 && vpt != 16) vpt = 16;
+    if (variant == 0 && vpt == 3) vpt = 4;
+    if (variant == 3) {  // bulk chunks: 256 threads, vpt = units (4 KB each) per chunk, <= 12 (48 KB)
+        threads = 256;
+        vpt = g_tuning.vpt > 0 ? (g_tuning.vpt > 12 ? 12 : g_tuning.vpt) : 8;
+    }
+    if (variant == 2) {  // TMA ring: 256 consumers, unit = 256 * vpu vectors
+        threads = kTmaConsumers;
+        vpt = (g_tuning.vpt == 4) ? 4 : 2;
+    }
+    const int unit_vecs = variant == 2 ? threads * vpt : threads;
+    const int upr = (nvec_max + unit_vecs - 1) / unit_vecs;  // units per row
     const long long U = (long long)B * rows * upr;
     if (U > 0x3fffffffLL) return SD_ERR_UNSUPPORTED;
 
@@ -534,11 +858,7 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
     p.row_max = row_max;
     p.row_sumexp = row_sumexp;
     char* ws = reinterpret_cast<char*>(workspace);
-    p.tickets = reinterpret_cast<uint32_t*>(ws + w.tickets);
-    p.part_key = reinterpret_cast<uint32_t*>(ws + w.key);
-    p.part_pos = reinterpret_cast<int32_t*>(ws + w.pos);
-    p.part_m = reinterpret_cast<float*>(ws + w.m);
-    p.part_s = reinterpret_cast<float*>(ws + w.s);
+    p.part = reinterpret_cast<unsigned long long*>(ws);
     p.B = B;
     p.rows = rows;
     p.K = K;
@@ -552,15 +872,31 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
     p.threshold = threshold;
     p.inv_temperature = inv_temperature;
     p.scale_log2 = inv_temperature * 1.4426950408889634f;
+    p.trace = nullptr;
 
     unsigned grid;
-    if (variant == 1) {
-        int per_sm = persist_occupancy(logit_dtype, stats, vpt, threads);
-        if (g_ctas_per_sm > 0 && g_ctas_per_sm < per_sm) per_sm = g_ctas_per_sm;
+    int tma_stages = 0;
+    size_t tma_smem = 0;
+    if (variant == 1 || variant == 2) {
+        int per_sm;
+        int q_floor;
+        if (variant == 1) {
+            per_sm = persist_occupancy(logit_dtype, stats, vpt, threads);
+            if (g_ctas_per_sm > 0 && g_ctas_per_sm < per_sm) per_sm = g_ctas_per_sm;
+            q_floor = vpt;  // a CTA should own at least one full batch of loads
+        } else {
+            per_sm = g_ctas_per_sm > 0 ? (g_ctas_per_sm > 4 ? 4 : g_ctas_per_sm) : 2;
+            const size_t unit_bytes = (size_t)unit_vecs * 16;
+            const size_t budget = (size_t)(224 * 1024) / per_sm - 2048;  // static smem + reserve per CTA
+            tma_stages = (int)(budget / unit_bytes);
+            if (tma_stages > kTmaMaxStages) tma_stages = kTmaMaxStages;
+            if (tma_stages < 2) return SD_ERR_UNSUPPORTED;
+            tma_smem = (size_t)tma_stages * unit_bytes;
+            q_floor = 2;
+        }
         long long G = (long long)sm_count() * per_sm;
-        // a CTA should own at least vpt units (one full batch of loads), and a row may be shared by
-        // at most kMaxChunks - 2 CTAs (partial slots): q >= upr / (kMaxChunks - 2)
-        const int q_min = (upr + (kMaxChunks - 3)) / (kMaxChunks - 2) > vpt ? (upr + (kMaxChunks - 3)) / (kMaxChunks - 2) : vpt;
+        // a row may be shared by at most kMaxChunks - 2 CTAs (partial slots): q >= upr / (kMaxChunks - 2)
+        const int q_min = (upr + (kMaxChunks - 3)) / (kMaxChunks - 2) > q_floor ? (upr + (kMaxChunks - 3)) / (kMaxChunks - 2) : q_floor;
         if (G * q_min > U) G = U / q_min;
         if (G < 1) G = 1;
         p.q = (int)(U / G);
@@ -573,14 +909,41 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
             S = kMaxChunks;
             upc = (upr + S - 1) / S;
             S = (upr + upc - 1) / upc;
+            if (variant == 3 && upc > 12) variant = 0;  // chunk would not fit the shared-memory stage
         }
         p.S = S;
         p.units_per_chunk = upc;
         grid = (unsigned)((size_t)B * rows * S);
     }
 
+    if (variant == 0 && g_trace && (size_t)grid <= g_trace_ctas) p.trace = g_trace;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     cudaError_t e;
+    if (variant == 3) {
+        const size_t smem = (size_t)p.units_per_chunk * threads * 16;
+        if (stats) {
+            if (logit_dtype == SD_F32) e = launch_bulk_t<float, true>(p, grid, threads, smem, st);
+            else if (logit_dtype == SD_F16) e = launch_bulk_t<__half, true>(p, grid, threads, smem, st);
+            else e = launch_bulk_t<__nv_bfloat16, true>(p, grid, threads, smem, st);
+        } else {
+            if (logit_dtype == SD_F32) e = launch_bulk_t<float, false>(p, grid, threads, smem, st);
+            else if (logit_dtype == SD_F16) e = launch_bulk_t<__half, false>(p, grid, threads, smem, st);
+            else e = launch_bulk_t<__nv_bfloat16, false>(p, grid, threads, smem, st);
+        }
+        return to_status(e);
+    }
+    if (variant == 2) {
+        if (stats) {
+            if (logit_dtype == SD_F32) e = launch_tma_t<float, true>(p, grid, vpt, tma_stages, tma_smem, st);
+            else if (logit_dtype == SD_F16) e = launch_tma_t<__half, true>(p, grid, vpt, tma_stages, tma_smem, st);
+            else e = launch_tma_t<__nv_bfloat16, true>(p, grid, vpt, tma_stages, tma_smem, st);
+        } else {
+            if (logit_dtype == SD_F32) e = launch_tma_t<float, false>(p, grid, vpt, tma_stages, tma_smem, st);
+            else if (logit_dtype == SD_F16) e = launch_tma_t<__half, false>(p, grid, vpt, tma_stages, tma_smem, st);
+            else e = launch_tma_t<__nv_bfloat16, false>(p, grid, vpt, tma_stages, tma_smem, st);
+        }
+        return to_status(e);
+    }
     if (stats) {
         if (logit_dtype == SD_F32) e = launch_t<float, true>(p, variant, grid, threads, vpt, st);
         else if (logit_dtype == SD_F16) e = launch_t<__half, true>(p, variant, grid, threads, vpt, st);
@@ -614,14 +977,20 @@ int sd_verify_set_tuning(int threads, int vectors_per_thread) {
     }
     if (threads < 32 || threads > 1024 || threads % 32) return SD_ERR_INVALID_ARG;
     int v = vectors_per_thread;
-    if (v != 1 && v != 2 && v != 4 && v != 8 && v != 16) return SD_ERR_INVALID_ARG;
+    if (v < 1 || v > 16) return SD_ERR_INVALID_ARG;  // each variant rounds to what it was built for
     if (threads > 512) return SD_ERR_INVALID_ARG;  // register budget (stats / 8+-vector kernels are built for <= 512)
     sd::g_tuning = {threads, v};
     return SD_OK;
 }
 
+int sd_verify_set_trace(void* device_buffer, size_t capacity_ctas) {
+    sd::g_trace = reinterpret_cast<unsigned long long*>(device_buffer);
+    sd::g_trace_ctas = device_buffer ? capacity_ctas : 0;
+    return SD_OK;
+}
+
 int sd_verify_set_variant(int variant, int ctas_per_sm) {
-    if (variant < 0 || variant > 1 || ctas_per_sm < 0 || ctas_per_sm > 32) return SD_ERR_INVALID_ARG;
+    if (variant < 0 || variant > 3 || ctas_per_sm < 0 || ctas_per_sm > 32) return SD_ERR_INVALID_ARG;
     sd::g_variant = variant;
     sd::g_ctas_per_sm = ctas_per_sm;
     return SD_OK;

@@ -18,7 +18,7 @@ from . import build as _build
 DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
 ID_I32, ID_I64 = 0, 1
 ACCEPT_GREEDY, ACCEPT_TYPICAL, ACCEPT_CONFIDENCE = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _vp = C.c_void_p
 _i = C.c_int
@@ -40,8 +40,9 @@ SIGNATURES = {
                             _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp]),
     "sd_verify_set_tuning": (_i, [_i, _i]),
     "sd_verify_set_variant": (_i, [_i, _i]),
+    "sd_verify_set_trace": (_i, [_vp, _sz]),
     "sd_kv_append": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp,
-                          _i, _vp, _i, _i64, _vp, _vp, _vp]),
+                          _i, _vp, _i, _i64, _vp, _vp, _i, _vp]),
     "sd_kv_append_layer": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                                 _vp, _i, _vp, _i, _vp, _vp]),
     "sd_kv_set_variant": (_i, [_i]),

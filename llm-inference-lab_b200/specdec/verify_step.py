@@ -41,6 +41,7 @@ class VerifyStep:
         self.device = torch.device(device)
         self.arena = arena
         self.mode, self.threshold, self.temperature = mode, threshold, temperature
+        self.rows_ready_early = False
         dev = self.device
         self.logits = torch.zeros((batch, k_draft + 1, vocab), dtype=logits_dtype, device=dev)
         self.draft_ids = torch.zeros((batch, k_draft), dtype=id_dtype, device=dev)
@@ -71,7 +72,11 @@ class VerifyStep:
         )
         if self.arena is not None:
             # keep accept_len drafts + the token they were conditioned on (row 0 of the pass)
-            self.arena.append(self.accept_len, keep_bias=1, zero_rejected=True, check_capacity=False)
+            # (the staged K/V rows come from the target forward, i.e. from before the verify launch, so
+            # rows_ready_early would be legal here; measured on B200 it buys nothing -- the verify CTAs
+            # hold the registers until the very end -- and it reads the rejected rows too)
+            self.arena.append(self.accept_len, keep_bias=1, zero_rejected=True, check_capacity=False,
+                              rows_ready_early=self.rows_ready_early)
 
     # -- CUDA graph (reference: src/specdec/utils/graph_capture.py:49-99 GraphCapture, never wired in) --
     def capture(self) -> None:

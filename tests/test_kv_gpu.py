@@ -119,7 +119,8 @@ def test_empty_cases():
     assert ok3.shape == (0, 2, 6, 8)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3, (3, "early"), 3 + 16 * 2, (3 + 16 * 2, "early")],
+                         ids=["vec", "bulk", "column", "column_early_rows", "column_rb2", "column_rb2_early_rows"])
 @pytest.mark.parametrize("zero_rejected", [True, False])
 def test_arena_all_layers_vs_oracle(variant, zero_rejected):
     """sd_kv_append over every layer with ragged lengths and device-side accept lengths."""
@@ -131,6 +132,8 @@ def test_arena_all_layers_vs_oracle(variant, zero_rejected):
     lens = torch.tensor([0, 7, 33, 20, 1], dtype=torch.int32)
     arena.set_lengths(lens)
     exp_k, exp_v = to_np(arena.k).copy(), to_np(arena.v).copy()
+    early = isinstance(variant, tuple)
+    variant = variant[0] if early else variant
     try:
         cuda_ops.set_kv_variant(variant)
         cur = lens.numpy().copy()
@@ -144,7 +147,9 @@ def test_arena_all_layers_vs_oracle(variant, zero_rejected):
             accept_dev = accept.cuda()
             if not fits.all():
                 break
-            arena.append(accept_dev, keep_bias=1, zero_rejected=zero_rejected)
+            if early:  # contract of rows_ready_early: the staged rows were not written by the previous kernel
+                torch.cuda.synchronize()
+            arena.append(accept_dev, keep_bias=1, zero_rejected=zero_rejected, rows_ready_early=early)
             nk, nv = to_np(arena.new_k), to_np(arena.new_v)
             for l in range(nl):
                 new_lens = c_oracle.kv_arena_append(exp_k[l], cur, nk[l], accept.numpy() + 1, zero_rejected)

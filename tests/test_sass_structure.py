@@ -1,0 +1,44 @@
+"""Build-time evidence read from the SASS of the in-tree library (no GPU needed; needs cuobjdump).
+
+ptxas decides on its own whether the VPT independent 128-bit loads of the verify kernel's batch stay
+ahead of their first use; once it serialised load -> use (one request in flight per thread) after a
+harmless refactor and the kernel lost 20 % of its bandwidth.  The launch bounds in sd_verify.cu pin the
+schedule; this test keeps it pinned."""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from kernels import build
+
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+
+
+def _sass(fun: str) -> str:
+    lib = build.build_cuda_kernels()
+    r = subprocess.run([CUOBJDUMP, "-sass", "-fun", fun, str(lib)], capture_output=True, text=True)
+    if r.returncode != 0 or "Function" not in r.stdout:
+        pytest.skip(f"cuobjdump could not list {fun}")
+    return r.stdout
+
+
+@pytest.mark.skipif(not shutil.which(CUOBJDUMP), reason="cuobjdump not installed")
+@pytest.mark.parametrize("vpt,need", [(4, 4), (8, 4)])
+def test_verify_kernel_keeps_its_load_batch_in_flight(vpt, need):
+    sass = _sass(f"_ZN2sd13verify_kernelI13__nv_bfloat16Li{vpt}ELb0EEEvNS_12VerifyParamsE")
+    ops = re.findall(r"(LDG\.E\.NA\.128|HMNMX2)", sass)
+    assert ops.count("LDG.E.NA.128") == vpt, "unexpected unrolling of the load batch"
+    first_use = ops.index("HMNMX2")
+    assert first_use >= need, f"only {first_use} of {vpt} streaming loads are issued before the first use: {''.join('L' if o.startswith('LDG') else 'm' for o in ops)}"
+
+
+@pytest.mark.skipif(not shutil.which(CUOBJDUMP), reason="cuobjdump not installed")
+def test_blackwell_native_instructions_present():
+    """TMA bulk copies (UBLKCP), mbarrier waits (SYNCS), PDL (ACQBULK/PREEXIT), tensor-core MMA (HMMA)
+    and ldmatrix (LDSM) must be in the library -- the evidence table of B200_PROFILING.md."""
+    lib = build.build_cuda_kernels()
+    r = subprocess.run([CUOBJDUMP, "-sass", str(lib)], capture_output=True, text=True)
+    assert r.returncode == 0
+    for mnemonic in ("UBLKCP", "SYNCS", "ACQBULK", "PREEXIT", "HMMA.16816.F32.BF16", "LDSM", "LDGSTS"):
+        assert mnemonic in r.stdout, f"{mnemonic} not found in the SASS of {lib}"

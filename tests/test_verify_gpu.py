@@ -13,6 +13,14 @@ from helpers import from_np, make_verify_inputs, np_dtype_name, to_np
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=[0, 1, 2, 3], ids=["tiled", "persistent", "tma_ring", "bulk_chunk"])
+def verify_variant(request):
+    """Every test runs under the three kernel variants (include/sd_verify.h: sd_verify_set_variant)."""
+    cuda_ops.set_verify_variant(request.param, 0)
+    yield request.param
+    cuda_ops.set_verify_variant(0, 0)
+
+
 def _check_bonus(logits, ids):
     acc, mask, tgt, bonus, packed = cuda_ops.verify_prefix_bonus_cuda(logits, ids)
     torch.cuda.synchronize()

@@ -10,6 +10,14 @@ from oracle import specdec_oracle as O
 from helpers import make_verify_inputs, to_np
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=[0, 1, 2, 3], ids=["tiled", "persistent", "tma_ring", "bulk_chunk"])
+def verify_variant(request):
+    """Every test runs under the three kernel variants (include/sd_verify.h: sd_verify_set_variant)."""
+    cuda_ops.set_verify_variant(request.param, 0)
+    yield request.param
+    cuda_ops.set_verify_variant(0, 0)
 RTOL, ATOL = 2e-4, 1e-6
 
 

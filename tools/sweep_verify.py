@@ -72,6 +72,7 @@ def main():
     ap.add_argument("--pdl", type=int, default=1)
     ap.add_argument("--single-graphs", action="store_true", help="one graph per launch (no PDL edges)")
     ap.add_argument("--quick", action="store_true", help="few configurations")
+    ap.add_argument("--tma", action="store_true", help="only the TMA-ring verify variant sweep")
     ap.add_argument("--stats", action="store_true")
     args = ap.parse_args()
     global GROUP
@@ -93,9 +94,14 @@ def main():
     if not args.skip_verify:
         # (variant, ctas_per_sm, threads, vpt): 1 = persistent equal-range grid, 0 = CTA per (row, chunk)
         configs = [(1, 0, 0, 0), (0, 0, 0, 0)]
+        # variant 2 (TMA ring): vpt = vectors per thread per ring slot (2 -> 8 KB, 4 -> 16 KB), cps = CTAs per SM
+        configs += [(2, c, 256, v) for v in (2, 4) for c in (1, 2, 3)]
+        configs += [(3, 0, 256, v) for v in (4, 6, 7, 8, 9, 11, 12)]
+        if args.tma:
+            configs = [(0, 0, 0, 0)] + [(2, c, 256, v) for v in (2, 4) for c in (1, 2, 3, 4)] + [(3, 0, 256, v) for v in (4, 6, 7, 8, 9, 11, 12)]
         if not args.quick:
             configs += [(1, c, t, v) for t in (256, 512) for v in (2, 4) for c in (0, 4) if not (t == 512 and c == 4)]
-            configs += [(0, 0, t, v) for t in (128, 256, 512) for v in (4, 8, 16)]
+            configs += [(0, 0, t, v) for t in (128, 256, 512) for v in (4, 5, 6, 7, 8, 16)]
         for (var, cps, t, v) in configs:
             try:
                 cuda_ops.set_verify_variant(var, cps)
