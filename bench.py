@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--tuning", default="", help="threads,vectors_per_thread for the verify kernel (sweeps)")
     ap.add_argument("--kv-variant", type=int, default=0)
     ap.add_argument("--batch", type=int, default=CFG["B"], help="sequences per GPU")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: fused peer-memory exchange in the verify kernel (default) or one NCCL all-gather per step")
     return ap.parse_args()
 
 
@@ -218,7 +220,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from kernels import cuda_ops
-    from scheduler.batch_shard import BatchShard, StepResultExchange
+    from scheduler.batch_shard import BatchShard, PeerExchange, StepResultExchange
     from specdec.cache.kv_arena import KVArena
     from specdec.verify_step import VerifyStep
 
@@ -248,11 +250,28 @@ def run_ours(args):
     arena = KVArena(CFG["layers"], B, CFG["Hkv"], CFG["D"], capacity, R, torch.bfloat16, dev)
     arena.set_lengths([CFG["L"]] * B)
 
+    shard = BatchShard(B * world, world, rank)
+    exch = peer = None
+    exchange_kind = "none"
+    if world > 1:
+        if args.exchange == "peer":
+            try:
+                peer = PeerExchange(shard, K, dev)
+                exchange_kind = "peer-memory stores from the verify kernel + 1-CTA wait kernel"
+            except Exception as e:  # noqa: BLE001  (CUDA IPC unavailable in this container)
+                print(f"[rank {rank}] PeerExchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr, flush=True)
+        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            peer = None
+            exch = StepResultExchange(shard, K, dev)
+            exchange_kind = "ncclAllGather of the packed records"
+
     # NB rotating input sets; each set has its own VerifyStep (static buffers) sharing one arena
     steps, stage_k, stage_v = [], [], []
     g = torch.Generator(device=dev).manual_seed(SEED + rank)
     for i in range(NB):
-        st = VerifyStep(B, K, V, arena=None, device=dev)
+        st = VerifyStep(B, K, V, arena=None, device=dev, exchange=peer)
         lg, ids = make_inputs(B, K, V, CFG["p_match"], SEED + 17 * rank + i, dev)
         st.logits.copy_(lg)
         st.draft_ids.copy_(ids)
@@ -261,15 +280,14 @@ def run_ours(args):
         stage_k.append(torch.randn(arena.new_k.shape, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16))
         stage_v.append(torch.randn(arena.new_v.shape, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16))
     tables = [arena._build_table(stage_k[i], stage_v[i]) for i in range(NB)]
-    shard = BatchShard(B * world, world, rank)
-    exch = StepResultExchange(shard, K, dev) if world > 1 else None
-
     def one_step(i):
         st = steps[i]
         st.run()
         arena.layer_table = tables[i]
         arena.append(st.accept_len, keep_bias=1, zero_rejected=True, check_capacity=False)
-        if exch is not None:
+        if peer is not None:
+            peer.wait()
+        elif exch is not None:
             exch.all_gather(st.packed)
 
     # warm every buffer set eagerly, then capture (a) one graph per buffer set and (b) one GROUP graph
@@ -342,7 +360,11 @@ def run_ours(args):
         arena.layer_table = tables[i]
         arena.append(steps[i].accept_len, keep_bias=1, zero_rejected=True, check_capacity=False)
 
+    for st in steps:  # the kernel alone: without the peer stores (they need a matching wait on every rank)
+        st.exchange = None
     verify_ms = isolate(lambda i: steps[i].run(), args.steps)
+    for st in steps:
+        st.exchange = peer
     arena.set_lengths([CFG["L"]] * B)
     kv_ms = isolate(kv_only, args.steps)
 
@@ -429,8 +451,11 @@ def run_ours(args):
             "config": workload_config(args, world),
             "tokens_per_step": tokens_per_step_all, "positions_per_s": B * world * R / (step_ms * 1e-3),
             "mean_accept_len": mean_keep - 1.0,
-            "gpu_launches": args.steps * 2,
-            "launches_per_step": {"sd_verify_kernel": 1, "sd_kv_append_kernel": 1, "nccl_allgather": 1 if world > 1 else 0},
+            "gpu_launches": args.steps * (3 if peer is not None else 2),
+            "launches_per_step": {"sd_verify_kernel": 1, "sd_kv_append_kernel": 1,
+                                  "sd_exchange_wait_kernel": 1 if peer is not None else 0,
+                                  "nccl_allgather": 1 if exch is not None else 0},
+            "exchange": exchange_kind,
             "roofline": {"bound": "hbm", "kernel": "verify_kernel<bf16>", "achieved": v_gbs, "peak": peak, "unit": "GB/s",
                          "frac": v_gbs / peak, "frac_of_8TBs_nominal": v_gbs / 8000.0, "traffic": traffic.get("verify_kernel"),
                          "algorithmic_bytes": verify_bytes, "us_per_launch": verify_ms * 1e3, "peak_source": peak_src},
@@ -461,8 +486,12 @@ def run_ours(args):
             }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: destroying a communicator whose collectives are still held by
+        # live CUDA graphs has been seen to hang (round 1, N=2: the JSON line was out, the exit never came).
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

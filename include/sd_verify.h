@@ -62,6 +62,44 @@ int sd_set_pdl(int enabled);
 int sd_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* ------------------------------------------------------------------------------------------
+ * Multi-GPU result exchange over peer memory (batch-sharded step, one process per GPU).
+ *
+ * No reference counterpart: the reference is single-device.  Sequences are
+ * independent, so ranks only exchange the packed [B_local, K+2] verify records.  Instead of a NCCL
+ * all-gather launch per step, the verify kernel's sequence finalizer stores each record straight into
+ * EVERY rank's exchange buffer (st.global on CUDA-IPC mapped peer pointers, NVLink) and bumps a
+ * per-parity arrival counter there with a system-scope release; sd_exchange_wait spins on the local
+ * counter, copies the gathered records out and advances the device-side epoch.  Records are double
+ * buffered by epoch parity: a rank can be at most one step ahead of its slowest peer.
+ *
+ * Exchange buffer (identical on every rank, sd_exchange_bytes): 256-byte header {u32 epoch,
+ * u32 arrived[2]} + int32 records[2][world * rows_per_rank][width].  The descriptor lives in DEVICE
+ * memory; peer[rank] is the rank's own buffer.
+ */
+#define SD_MAX_PEERS 16
+typedef struct sd_exchange {
+    int32_t world, rank;
+    int32_t rows_per_rank; /* record rows reserved per rank (max local batch) */
+    int32_t width;         /* K + 2 */
+    int32_t total_rows;    /* sum of the local batches of all ranks = records arriving per step */
+    int32_t reserved[3];
+    void* peer[SD_MAX_PEERS];
+} sd_exchange;
+
+size_t sd_exchange_bytes(int world, int rows_per_rank, int width);
+/* cudaMalloc + zero an exchange buffer on the current device; handle_out receives the 64-byte
+ * cudaIpcMemHandle_t to send to the other ranks (nullable). */
+int sd_exchange_alloc(size_t bytes, void** ptr_out, void* handle_out);
+/* Map a peer's buffer from its 64-byte handle (cudaIpcOpenMemHandle, lazy peer access). */
+int sd_exchange_open(const void* handle, void** peer_ptr_out);
+int sd_exchange_close(void* peer_ptr);
+int sd_exchange_free(void* ptr);
+/* Wait until every rank's records of the current epoch have arrived in this rank's buffer, copy
+ * them to out [world * rows_per_rank, width] int32 (nullable) and advance the epoch.  One small
+ * kernel on `stream`; call it once per verify launch that carried `exchange`. */
+int sd_exchange_wait(const sd_exchange* exchange, int32_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Kernel 1: fused verify.
  *
  * Replaces  verify_prefix(logits[B,K,V], draft_ids[B,K]) -> (accept_len[B] i32, mask[B,K] u8)
@@ -81,7 +119,10 @@ int sd_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * bonus       [B] int32                 (nullable)  target_ids[b, accept_len[b]] (rows == K+1) else -1
  * packed      [B, K + 2] int32          (nullable)  {accept_len, target_ids[0..K]} -- the record the
  *                                        multi-GPU allgather exchanges (target_ids[K] = -1 if rows == K)
- * workspace   sd_verify_workspace_bytes(B, rows) bytes, zeroed once with sd_verify_workspace_init;
+ * exchange    (nullable, device pointer) when set, the finalizer of sequence b also stores the packed
+ *             record into row rank * rows_per_rank + b of every peer's exchange buffer (see above);
+ *             requires width == K + 2 and B <= rows_per_rank
+ * workspace   sd_verify_workspace_bytes(B, rows) bytes, 8-byte aligned, zeroed once with sd_verify_workspace_init;
  *             the kernel leaves it zeroed again, so one init serves any number of launches
  *             (including graph replays).  Must not be shared by launches that may overlap.
  *
@@ -94,7 +135,7 @@ int sd_verify_prefix(const void* logits, int logit_dtype, int64_t stride_b, int6
                      const void* draft_ids, int id_dtype, int64_t id_stride_b,
                      int32_t* accept_len, uint8_t* accepted_mask, int32_t* target_ids,
                      int32_t* bonus, int32_t* packed, void* workspace, size_t workspace_bytes,
-                     int B, int rows, int K, int V, void* stream);
+                     int B, int rows, int K, int V, void* stream, const sd_exchange* exchange);
 
 /*
  * Same pass with softmax statistics ("sampling mode"): one read of the logits yields, per row,
@@ -115,7 +156,8 @@ int sd_verify_step(const void* logits, int logit_dtype, int64_t stride_b, int64_
                    float threshold, float inv_temperature, int32_t* accept_len,
                    uint8_t* accepted_mask, int32_t* target_ids, int32_t* bonus, int32_t* packed,
                    float* token_prob, float* row_max, float* row_sumexp, void* workspace,
-                   size_t workspace_bytes, int B, int rows, int K, int V, void* stream);
+                   size_t workspace_bytes, int B, int rows, int K, int V, void* stream,
+                   const sd_exchange* exchange);
 
 /* Tuning hook used by tools/ and bench.py sweeps: threads per CTA (128..1024, multiple of 32),
  * 16-byte vectors in flight per thread (1..16), 0 restores the built-in heuristic. */

@@ -5,11 +5,15 @@
 //
 // Work decomposition.  A logits row is cut into UNITS of blockDim.x 16-byte vectors (one vector per
 // thread).  A CTA reduces a SEGMENT = a run of consecutive units of one row:
-//   variant 1 "persistent" (default): grid = SMs x resident CTAs; the B*rows*units_per_row units are
+//   variant 3 "bulk chunk" (default): one CTA per (row, chunk of <= 12 units); thread 0 fetches the
+//           whole chunk with ONE cp.async.bulk (TMA 1-D) into shared memory, every thread waits on the
+//           mbarrier and folds its vectors from shared memory.
+//   variant 1 "persistent": grid = SMs x resident CTAs; the B*rows*units_per_row units are
 //           split into gridDim.x contiguous, equal (+-1 unit) ranges, so every SM streams the same
 //           number of bytes and there is no partial last wave; a range that crosses a row boundary is
 //           processed as two segments.
-//   variant 0 "tiled": one CTA per (row, chunk of VPT units) -- the first version, kept for sweeps.
+//   variant 0 "tiled": one CTA per (row, chunk of VPT units), register-staged 128-bit loads.
+//   variant 2 "tma ring": persistent grid, producer warp + mbarrier ring of cp.async.bulk copies.
 // Per segment:
 //   thread: 128-bit ld.global.nc loads, VPT of them issued before first use; running packed max
 //           (max.NaN.{bf16x2,f16x2,f32}) + the index of the FIRST vector at which its maximum
@@ -31,13 +35,14 @@
 namespace sd {
 
 constexpr int kMaxChunks = 64;  // upper bound of S (partials per row) -> workspace size
+constexpr int kExchangeHeader = 256;  // bytes before the records of an exchange buffer
 
 struct VerifyTuning {
     int threads;
     int vpt;
 };
 static VerifyTuning g_tuning = {0, 0};
-static int g_variant = 0;       // 0 tiled (default: measured faster), 1 persistent
+static int g_variant = 3;       // default: bulk chunks (fastest measured, schedule independent of ptxas)
 static unsigned long long* g_trace = nullptr;  // device buffer for per-CTA timestamps (variant 0 only)
 static size_t g_trace_ctas = 0;
 static int g_ctas_per_sm = 0;   // persistent grid = SMs * this (0 = occupancy)
@@ -68,6 +73,7 @@ struct VerifyParams {
     int mode;
     float threshold, scale_log2;  // scale_log2 = inv_temperature * log2(e)
     float inv_temperature;
+    const sd_exchange* xchg;    // nullable: peer-memory result exchange (device memory)
     unsigned long long* trace;  // evidence runs: [grid][4] = {globaltimer at entry, after the scan, at exit, smid}
 };
 
@@ -210,6 +216,11 @@ SD_DEVINL Cand exact_in_vector(const uint4& v, int pos0) {
 SD_DEVINL unsigned long long ld_volatile_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+SD_DEVINL unsigned ld_volatile_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 SD_DEVINL void st_volatile_u64(unsigned long long* p, unsigned long long v) {
@@ -426,6 +437,27 @@ SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int n
         if (lane == 0) {
             p.accept_len[b] = nacc;
             if (p.bonus) p.bonus[b] = p.rows > p.K ? s_tgt[nacc] : -1;
+        }
+        if (p.xchg) {
+            // fused result exchange: the record goes straight into every rank's buffer over NVLink
+            const sd_exchange* x = p.xchg;
+            const int world = x->world, width = x->width;
+            char* own = reinterpret_cast<char*>(x->peer[x->rank]);
+            const unsigned epoch = ld_volatile_u32(reinterpret_cast<const unsigned*>(own));
+            const unsigned parity = epoch & 1u;
+            const size_t rec_row = (size_t)parity * world * x->rows_per_rank + (size_t)x->rank * x->rows_per_rank + b;
+            for (int i = lane; i < world * width; i += 32) {
+                const int pr = i / width, col = i - pr * width;
+                int val = -1;
+                if (col == 0) val = nacc;
+                else if (col - 1 < p.rows) val = s_tgt[col - 1];
+                int32_t* recs = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(x->peer[pr]) + kExchangeHeader);
+                recs[rec_row * width + col] = val;
+            }
+            __threadfence_system();  // the records are visible system-wide before they are counted
+            __syncwarp();
+            if (lane < world)
+                atomicAdd_system(reinterpret_cast<unsigned*>(reinterpret_cast<char*>(x->peer[lane]) + 4 + 4 * parity), 1u);
         }
     }
     cta_sync<NAMED>(nthreads);  // s_tgt and the reduce scratch are reused by the caller's next segment
@@ -798,7 +830,7 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
                       float inv_temperature, int32_t* accept_len, uint8_t* accepted_mask,
                       int32_t* target_ids, int32_t* bonus, int32_t* packed, float* token_prob,
                       float* row_max, float* row_sumexp, void* workspace, size_t workspace_bytes, int B,
-                      int rows, int K, int V, void* stream) {
+                      int rows, int K, int V, void* stream, const sd_exchange* exchange) {
     if (B < 0 || K < 0 || V <= 0 || rows <= 0) return SD_ERR_INVALID_ARG;
     if (rows != K && rows != K + 1) return SD_ERR_SHAPE;
     if (rows > 64) return SD_ERR_UNSUPPORTED;
@@ -831,7 +863,14 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
     if (variant == 0 && vpt == 3) vpt = 4;
     if (variant == 3) {  // bulk chunks: 256 threads, vpt = units (4 KB each) per chunk, <= 12 (48 KB)
         threads = 256;
-        vpt = g_tuning.vpt > 0 ? (g_tuning.vpt > 12 ? 12 : g_tuning.vpt) : 8;
+        if (g_tuning.vpt > 0) {
+            vpt = g_tuning.vpt > 12 ? 12 : g_tuning.vpt;
+        } else {
+            // 36 KB chunks (measured best at B=64, V=128256); smaller ones while the grid would leave SMs idle
+            vpt = 9;
+            const int upr3 = (nvec_max + threads - 1) / threads;
+            while (vpt > 2 && (long long)B * rows * ((upr3 + vpt - 1) / vpt) < 2LL * sm_count()) --vpt;
+        }
     }
     if (variant == 2) {  // TMA ring: 256 consumers, unit = 256 * vpu vectors
         threads = kTmaConsumers;
@@ -873,6 +912,7 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
     p.inv_temperature = inv_temperature;
     p.scale_log2 = inv_temperature * 1.4426950408889634f;
     p.trace = nullptr;
+    p.xchg = exchange;
 
     unsigned grid;
     int tma_stages = 0;
@@ -999,21 +1039,23 @@ int sd_verify_set_variant(int variant, int ctas_per_sm) {
 int sd_verify_prefix(const void* logits, int logit_dtype, int64_t stride_b, int64_t stride_r,
                      const void* draft_ids, int id_dtype, int64_t id_stride_b, int32_t* accept_len,
                      uint8_t* accepted_mask, int32_t* target_ids, int32_t* bonus, int32_t* packed,
-                     void* workspace, size_t workspace_bytes, int B, int rows, int K, int V, void* stream) {
+                     void* workspace, size_t workspace_bytes, int B, int rows, int K, int V, void* stream,
+                     const sd_exchange* exchange) {
     return sd::run_verify(false, logits, logit_dtype, stride_b, stride_r, draft_ids, id_dtype, id_stride_b,
                           SD_ACCEPT_GREEDY, 0.f, 1.f, accept_len, accepted_mask, target_ids, bonus, packed,
-                          nullptr, nullptr, nullptr, workspace, workspace_bytes, B, rows, K, V, stream);
+                          nullptr, nullptr, nullptr, workspace, workspace_bytes, B, rows, K, V, stream, exchange);
 }
 
 int sd_verify_step(const void* logits, int logit_dtype, int64_t stride_b, int64_t stride_r,
                    const void* draft_ids, int id_dtype, int64_t id_stride_b, int mode, float threshold,
                    float inv_temperature, int32_t* accept_len, uint8_t* accepted_mask, int32_t* target_ids,
                    int32_t* bonus, int32_t* packed, float* token_prob, float* row_max, float* row_sumexp,
-                   void* workspace, size_t workspace_bytes, int B, int rows, int K, int V, void* stream) {
+                   void* workspace, size_t workspace_bytes, int B, int rows, int K, int V, void* stream,
+                   const sd_exchange* exchange) {
     if (!(inv_temperature > 0.f)) return SD_ERR_INVALID_ARG;
     return sd::run_verify(true, logits, logit_dtype, stride_b, stride_r, draft_ids, id_dtype, id_stride_b, mode,
                           threshold, inv_temperature, accept_len, accepted_mask, target_ids, bonus, packed,
-                          token_prob, row_max, row_sumexp, workspace, workspace_bytes, B, rows, K, V, stream);
+                          token_prob, row_max, row_sumexp, workspace, workspace_bytes, B, rows, K, V, stream, exchange);
 }
 
 }  // extern "C"

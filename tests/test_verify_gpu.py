@@ -15,10 +15,10 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(autouse=True, params=[0, 1, 2, 3], ids=["tiled", "persistent", "tma_ring", "bulk_chunk"])
 def verify_variant(request):
-    """Every test runs under the three kernel variants (include/sd_verify.h: sd_verify_set_variant)."""
+    """Every test runs under the four kernel variants (include/sd_verify.h: sd_verify_set_variant)."""
     cuda_ops.set_verify_variant(request.param, 0)
     yield request.param
-    cuda_ops.set_verify_variant(0, 0)
+    cuda_ops.set_verify_variant()
 
 
 def _check_bonus(logits, ids):

@@ -4,6 +4,7 @@ import pytest
 import torch
 
 from oracle import c_oracle
+from oracle import specdec_oracle as O
 from specdec.cache.kv_arena import KVArena
 from specdec.verify_step import VerifyStep
 from helpers import make_verify_inputs, to_np
@@ -93,3 +94,35 @@ def test_advance_sequences_on_device_from_packed():
         got = tokens[b, int(lengths[b]) : int(new_len[b])].cpu().tolist()
         assert got == tgt[b, : acc[b] + 1].tolist() and got[-1] == bonus[b]
         assert got[:-1] == to_np(ids)[b, : acc[b]].tolist()  # accepted tokens are the draft tokens
+
+
+@pytest.mark.parametrize("world,global_batch", [(1, 6), (2, 8), (4, 10)])
+def test_peer_exchange_emulated_ranks(world, global_batch):
+    """Fused result exchange: every rank's verify kernel writes its packed records into all ranks'
+    exchange buffers; wait() returns the gathered [global_batch, K+2] table on every rank.  Ranks are
+    emulated inside one process (all verifies are launched before any wait, so nothing spins on work
+    that has not been launched); uneven shards (10 over 4) exercise the padding; several steps exercise
+    the parity double-buffering and the device-side epoch."""
+    from scheduler.batch_shard import PeerExchange
+
+    K, V = 4, 4099
+    xs = PeerExchange.emulate(world, global_batch, K, "cuda")
+    try:
+        steps = [VerifyStep(x.shard.local_batch, K, V, exchange=x) for x in xs]
+        for it in range(5):
+            logits, ids = make_verify_inputs(global_batch, K + 1, K, V, "bf16", p_match=0.6, seed=100 + it, device="cuda")
+            e_acc, _, e_tgt, _ = c_oracle.verify(to_np(logits), "bf16", to_np(ids))
+            want = O.pack_step_result(e_acc, e_tgt)
+            for x, st in zip(xs, steps):
+                s, e = x.shard.bounds()
+                if e > s:
+                    st.logits.copy_(logits[s:e])
+                    st.draft_ids.copy_(ids[s:e])
+                    st.run()
+            gathered = [x.wait().clone() for x in xs]
+            torch.cuda.synchronize()
+            for r, got in enumerate(gathered):
+                np.testing.assert_array_equal(got.cpu().numpy(), want, err_msg=f"rank {r} step {it}")
+    finally:
+        for x in xs:
+            x.close()

@@ -93,7 +93,7 @@ def main():
     results = []
     if not args.skip_verify:
         # (variant, ctas_per_sm, threads, vpt): 1 = persistent equal-range grid, 0 = CTA per (row, chunk)
-        configs = [(1, 0, 0, 0), (0, 0, 0, 0)]
+        configs = [(3, 0, 0, 0), (1, 0, 0, 0), (0, 0, 0, 0)]
         # variant 2 (TMA ring): vpt = vectors per thread per ring slot (2 -> 8 KB, 4 -> 16 KB), cps = CTAs per SM
         configs += [(2, c, 256, v) for v in (2, 4) for c in (1, 2, 3)]
         configs += [(3, 0, 256, v) for v in (4, 6, 7, 8, 9, 11, 12)]
@@ -112,7 +112,7 @@ def main():
                 print(json.dumps(results[-1]), flush=True)
             except Exception as e:  # noqa: BLE001
                 print(json.dumps({"kernel": "verify", "variant": var, "threads": t, "vpt": v, "error": str(e)[:200]}), flush=True)
-        cuda_ops.set_verify_variant(0, 0)
+        cuda_ops.set_verify_variant()
     # torch.argmax on the same buffers: the ATen incumbent (reference.py:37 on CUDA tensors)
     us = time_graphs([lambda s=s: torch.argmax(s.logits, dim=-1) for s in steps], args.iters)
     print(json.dumps({"kernel": "torch.argmax", "us": us, "GBps": nbytes / us / 1e3}), flush=True)
