@@ -257,7 +257,7 @@ def run_ours(args):
         if args.exchange == "peer":
             try:
                 peer = PeerExchange(shard, K, dev)
-                exchange_kind = "peer-memory stores from the verify kernel + 1-CTA wait kernel"
+                exchange_kind = "peer-memory stores from the verify kernel, confirmed + gathered by the last CTA of kv_append"
             except Exception as e:  # noqa: BLE001  (CUDA IPC unavailable in this container)
                 print(f"[rank {rank}] PeerExchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr, flush=True)
         ok = torch.tensor([1 if peer is not None else 0], device=dev)
@@ -272,6 +272,7 @@ def run_ours(args):
     g = torch.Generator(device=dev).manual_seed(SEED + rank)
     for i in range(NB):
         st = VerifyStep(B, K, V, arena=None, device=dev, exchange=peer)
+        st.exchange_wait = False  # the append below (shared arena) confirms and gathers the records
         lg, ids = make_inputs(B, K, V, CFG["p_match"], SEED + 17 * rank + i, dev)
         st.logits.copy_(lg)
         st.draft_ids.copy_(ids)
@@ -284,10 +285,10 @@ def run_ours(args):
         st = steps[i]
         st.run()
         arena.layer_table = tables[i]
-        arena.append(st.accept_len, keep_bias=1, zero_rejected=True, check_capacity=False)
-        if peer is not None:
-            peer.wait()
-        elif exch is not None:
+        # N>1, peer exchange: the last CTA of the append confirms + gathers the records the verify kernel
+        # pushed to every rank (no launch of its own)
+        arena.append(st.accept_len, keep_bias=1, zero_rejected=True, check_capacity=False, exchange=peer)
+        if exch is not None:
             exch.all_gather(st.packed)
 
     # warm every buffer set eagerly, then capture (a) one graph per buffer set and (b) one GROUP graph
@@ -451,9 +452,8 @@ def run_ours(args):
             "config": workload_config(args, world),
             "tokens_per_step": tokens_per_step_all, "positions_per_s": B * world * R / (step_ms * 1e-3),
             "mean_accept_len": mean_keep - 1.0,
-            "gpu_launches": args.steps * (3 if peer is not None else 2),
+            "gpu_launches": args.steps * 2,
             "launches_per_step": {"sd_verify_kernel": 1, "sd_kv_append_kernel": 1,
-                                  "sd_exchange_wait_kernel": 1 if peer is not None else 0,
                                   "nccl_allgather": 1 if exch is not None else 0},
             "exchange": exchange_kind,
             "roofline": {"bound": "hbm", "kernel": "verify_kernel<bf16>", "achieved": v_gbs, "peak": peak, "unit": "GB/s",

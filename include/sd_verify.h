@@ -67,14 +67,16 @@ int sd_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * No reference counterpart: the reference is single-device.  Sequences are
  * independent, so ranks only exchange the packed [B_local, K+2] verify records.  Instead of a NCCL
  * all-gather launch per step, the verify kernel's sequence finalizer stores each record straight into
- * EVERY rank's exchange buffer (st.global on CUDA-IPC mapped peer pointers, NVLink) and bumps a
- * per-parity arrival counter there with a system-scope release; sd_exchange_wait spins on the local
- * counter, copies the gathered records out and advances the device-side epoch.  Records are double
- * buffered by epoch parity: a rank can be at most one step ahead of its slowest peer.
+ * EVERY rank's exchange buffer (st.global on CUDA-IPC mapped peer pointers, NVLink).  Every value
+ * travels in ONE 8-byte store together with an epoch tag -- {epoch + 1, value} -- so the data path needs
+ * no fence, atomic or arrival counter: the consumer (the last CTA of sd_kv_append, or
+ * sd_exchange_wait) polls the words of the current epoch until their tags match, copies the values
+ * out and advances the device-side epoch.  Words are double buffered by epoch parity: a rank can be
+ * at most one step ahead of its slowest peer.
  *
- * Exchange buffer (identical on every rank, sd_exchange_bytes): 256-byte header {u32 epoch,
- * u32 arrived[2]} + int32 records[2][world * rows_per_rank][width].  The descriptor lives in DEVICE
- * memory; peer[rank] is the rank's own buffer.
+ * Exchange buffer (identical on every rank, sd_exchange_bytes): 256-byte header {u32 epoch} +
+ * u64 words[2][world * rows_per_rank][width].  The descriptor lives in DEVICE memory; peer[rank] is the
+ * rank's own buffer.  Rank r holds total_rows / world (+1 for the first total_rows % world ranks) rows.
  */
 #define SD_MAX_PEERS 16
 typedef struct sd_exchange {
@@ -212,6 +214,12 @@ typedef struct sd_kv_layer {
  *             max_seq_len_host >= 0; on device, rows that would fall beyond C are dropped and
  *             *overflow_flag (nullable, int32) is set non-zero.
  * ticket      one int32 in device memory, zero before the first launch (the kernel re-zeroes it).
+ * exchange / exchange_out  (nullable) multi-GPU step: the records that the verify launch of this step
+ *             pushed into every rank's exchange buffer are confirmed and gathered HERE, by the last
+ *             CTA to retire (arrival count of the current epoch reached -> copy the
+ *             [world * rows_per_rank, width] table to exchange_out -> advance the epoch), so the
+ *             exchange hides behind the append and needs no launch of its own.  Use this INSTEAD of
+ *             sd_exchange_wait for that step.
  * rows_ready_early  non-zero = the caller guarantees that the layer table and the offered rows were
  *             written at least two kernels before this call on the stream (in the verify step they
  *             come from the target forward; the kernel just before this one is the fused verify,
@@ -228,7 +236,7 @@ int sd_kv_append(const sd_kv_layer* layers, int n_layers, int B, int H, int R, i
                  const int32_t* seq_lens, int32_t* seq_lens_out, const int32_t* n_keep,
                  int keep_bias, const uint8_t* accepted_mask, int zero_rejected,
                  int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, int rows_ready_early,
-                 void* stream);
+                 void* stream, const sd_exchange* exchange, int32_t* exchange_out);
 
 /*
  * Single-layer form with the layer record passed by value and a uniform current length

@@ -164,6 +164,39 @@ SD_DEVINL int load_id(const void* ids, int id_dtype, int64_t i) {
     return (v < 0 || v > 0x7fffffffLL) ? -1 : (int)v;
 }
 
+// ---- peer-memory result exchange, consumer side (include/sd_verify.h: sd_exchange) ----
+// Exchange buffer: 256-byte header {u32 epoch} + u64 words[2][world * rows_per_rank][width], each word
+// {epoch + 1, value} written by ONE 8-byte store of the producing verify kernel.  Called by a whole CTA:
+// polls every expected word of the current epoch until its tag matches, writes the values to `out`
+// ([world * rows_per_rank, width] int32, nullable; rows beyond a rank's batch are left untouched), then
+// advances the epoch.  Rank r holds total_rows / world (+1 for the first total_rows % world ranks) rows.
+constexpr int kExchangeHeaderBytes = 256;
+SD_DEVINL void exchange_gather_cta(const sd_exchange* x, int32_t* out) {
+    char* own = reinterpret_cast<char*>(x->peer[x->rank]);
+    unsigned epoch;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(epoch) : "l"(own) : "memory");
+    const unsigned want = epoch + 1u;
+    const int world = x->world, rpr = x->rows_per_rank, width = x->width;
+    const int base = x->total_rows / world, extra = x->total_rows % world;
+    const unsigned long long* words =
+        reinterpret_cast<const unsigned long long*>(own + kExchangeHeaderBytes) + (size_t)(epoch & 1u) * world * rpr * width;
+    const int n = world * rpr * width;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int row = i / width;
+        const int r = row / rpr;
+        if (row - r * rpr >= base + (r < extra ? 1 : 0)) continue;  // padding row of an uneven shard
+        unsigned long long w;
+        for (;;) {
+            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(words + i) : "memory");
+            if ((unsigned)(w >> 32) == want) break;
+            __nanosleep(64);
+        }
+        if (out) out[i] = (int)(unsigned)w;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(own) = epoch + 1u;
+}
+
 inline int elt_size(int dtype) { return dtype == SD_F32 ? 4 : 2; }
 
 inline int to_status(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }

@@ -5,41 +5,11 @@
 
 namespace sd {
 
-constexpr int kExchangeHeaderBytes = 256;  // {u32 epoch, u32 arrived[2]}; must match sd_verify.cu
-
-SD_DEVINL unsigned ld_sys_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-SD_DEVINL int ld_sys_s32(const int32_t* p) {
-    int v;
-    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// One CTA.  Spins (with back-off) until all total_rows records of the current epoch have been counted
-// in this rank's buffer, copies them out, then advances the epoch for the next verify launch.
+// One CTA: gather the records of the current epoch (polls the tagged words), then advance the epoch.
 __global__ void __launch_bounds__(256) exchange_wait_kernel(const sd_exchange* x, int32_t* out) {
     pdl_wait();
     pdl_trigger();
-    char* own = reinterpret_cast<char*>(x->peer[x->rank]);
-    unsigned* hdr = reinterpret_cast<unsigned*>(own);
-    const unsigned epoch = ld_sys_u32(hdr);
-    const unsigned parity = epoch & 1u;
-    const unsigned target = (epoch / 2u + 1u) * (unsigned)x->total_rows;
-    if (threadIdx.x == 0) {
-        while ((int)(ld_sys_u32(hdr + 1 + parity) - target) < 0) __nanosleep(200);
-        __threadfence_system();
-    }
-    __syncthreads();
-    const int n = x->world * x->rows_per_rank * x->width;
-    if (out) {
-        const int32_t* recs = reinterpret_cast<const int32_t*>(own + kExchangeHeaderBytes) + (size_t)parity * n;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = ld_sys_s32(recs + i);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(hdr) = epoch + 1u;
+    exchange_gather_cta(x, out);
 }
 
 }  // namespace sd
@@ -48,7 +18,7 @@ extern "C" {
 
 size_t sd_exchange_bytes(int world, int rows_per_rank, int width) {
     if (world <= 0 || rows_per_rank <= 0 || width <= 0) return 0;
-    return (size_t)sd::kExchangeHeaderBytes + (size_t)2 * world * rows_per_rank * width * sizeof(int32_t);
+    return (size_t)sd::kExchangeHeaderBytes + (size_t)2 * world * rows_per_rank * width * sizeof(unsigned long long);
 }
 
 int sd_exchange_alloc(size_t bytes, void** ptr_out, void* handle_out) {

@@ -38,6 +38,8 @@ struct KvParams {
     int early_rows;  // column kernel: fetch the offered rows before griddepcontrol.wait
     int32_t* overflow;
     int32_t* ticket;
+    const sd_exchange* xchg;  // nullable: confirm + gather the verify records of this step (last CTA)
+    int32_t* xchg_out;
     unsigned total_ctas;
 };
 
@@ -88,6 +90,10 @@ SD_DEVINL void retire_and_commit(const KvParams& p) {
             p.seq_lens_out[b] = len + n;
         }
     }
+    // Fused result exchange (multi-GPU): the records the verify kernel pushed to every rank have had
+    // this whole kernel's duration to arrive; the last CTA polls the tagged words of the current epoch,
+    // copies the gathered table out and advances the epoch -- no separate wait launch.
+    if (p.xchg) exchange_gather_cta(p.xchg, p.xchg_out);
     __syncthreads();
     if (threadIdx.x == 0) *p.ticket = 0;
 }
@@ -351,7 +357,8 @@ static int kv_append_impl(const sd_kv_layer* layers, const sd_kv_layer* single, 
                           int64_t arena_stride_h, int64_t new_stride_b, int64_t new_stride_h,
                           int64_t new_stride_r, const int32_t* seq_lens, int32_t* seq_lens_out,
                           const int32_t* n_keep, int keep_bias, const uint8_t* accepted_mask, int zero_rejected,
-                          int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, int early_rows, void* stream) {
+                          int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, int early_rows, void* stream,
+                          const sd_exchange* exchange = nullptr, int32_t* exchange_out = nullptr) {
     using namespace sd;
     if (n_layers < 0 || B < 0 || H < 0 || R < 0 || row_bytes <= 0 || capacity < 0) return SD_ERR_INVALID_ARG;
     if (n_layers == 0 || B == 0 || H == 0) return SD_OK;
@@ -385,6 +392,8 @@ static int kv_append_impl(const sd_kv_layer* layers, const sd_kv_layer* single, 
     p.early_rows = early_rows ? 1 : 0;
     p.overflow = overflow_flag;
     p.ticket = ticket;
+    p.xchg = exchange;
+    p.xchg_out = exchange_out;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
     if (R == 0) {  // nothing offered: only the length commit (identity) is required
@@ -450,11 +459,14 @@ int sd_kv_append(const sd_kv_layer* layers, int n_layers, int B, int H, int R, i
                  int64_t capacity, int64_t arena_stride_b, int64_t arena_stride_h, int64_t new_stride_b,
                  int64_t new_stride_h, int64_t new_stride_r, const int32_t* seq_lens, int32_t* seq_lens_out,
                  const int32_t* n_keep, int keep_bias, const uint8_t* accepted_mask, int zero_rejected,
-                 int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, int rows_ready_early, void* stream) {
+                 int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, int rows_ready_early, void* stream,
+                 const sd_exchange* exchange, int32_t* exchange_out) {
     if (n_layers > 0 && !layers) return SD_ERR_INVALID_ARG;
+    if (exchange && (n_layers == 0 || B == 0 || H == 0 || R == 0)) return SD_ERR_UNSUPPORTED;  // nothing would launch
     return kv_append_impl(layers, nullptr, 0, n_layers, B, H, R, row_bytes, capacity, arena_stride_b, arena_stride_h,
                           new_stride_b, new_stride_h, new_stride_r, seq_lens, seq_lens_out, n_keep, keep_bias,
-                          accepted_mask, zero_rejected, max_seq_len_host, overflow_flag, ticket, rows_ready_early, stream);
+                          accepted_mask, zero_rejected, max_seq_len_host, overflow_flag, ticket, rows_ready_early, stream,
+                          exchange, exchange_out);
 }
 
 int sd_kv_append_layer(void* arena_k, void* arena_v, const void* new_k, const void* new_v, int B, int H, int R,

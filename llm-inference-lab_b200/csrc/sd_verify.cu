@@ -35,7 +35,7 @@
 namespace sd {
 
 constexpr int kMaxChunks = 64;  // upper bound of S (partials per row) -> workspace size
-constexpr int kExchangeHeader = 256;  // bytes before the records of an exchange buffer
+
 
 struct VerifyTuning {
     int threads;
@@ -439,25 +439,25 @@ SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int n
             if (p.bonus) p.bonus[b] = p.rows > p.K ? s_tgt[nacc] : -1;
         }
         if (p.xchg) {
-            // fused result exchange: the record goes straight into every rank's buffer over NVLink
+            // Fused result exchange: the record goes straight into every rank's buffer (NVLink stores on
+            // peer pointers).  Each value travels in ONE 8-byte store together with the epoch tag
+            // (LL-style: {epoch + 1, value}), so no fence, atomic or arrival counter is needed -- the
+            // consumer polls the words until their tag matches.
             const sd_exchange* x = p.xchg;
             const int world = x->world, width = x->width;
             char* own = reinterpret_cast<char*>(x->peer[x->rank]);
             const unsigned epoch = ld_volatile_u32(reinterpret_cast<const unsigned*>(own));
-            const unsigned parity = epoch & 1u;
-            const size_t rec_row = (size_t)parity * world * x->rows_per_rank + (size_t)x->rank * x->rows_per_rank + b;
+            const unsigned long long tag = (unsigned long long)(epoch + 1u) << 32;
+            const size_t rec_row = (size_t)(epoch & 1u) * world * x->rows_per_rank + (size_t)x->rank * x->rows_per_rank + b;
             for (int i = lane; i < world * width; i += 32) {
                 const int pr = i / width, col = i - pr * width;
                 int val = -1;
                 if (col == 0) val = nacc;
                 else if (col - 1 < p.rows) val = s_tgt[col - 1];
-                int32_t* recs = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(x->peer[pr]) + kExchangeHeader);
-                recs[rec_row * width + col] = val;
+                unsigned long long* recs =
+                    reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(x->peer[pr]) + kExchangeHeaderBytes);
+                st_volatile_u64(recs + rec_row * width + col, tag | (unsigned)val);
             }
-            __threadfence_system();  // the records are visible system-wide before they are counted
-            __syncwarp();
-            if (lane < world)
-                atomicAdd_system(reinterpret_cast<unsigned*>(reinterpret_cast<char*>(x->peer[lane]) + 4 + 4 * parity), 1u);
         }
     }
     cta_sync<NAMED>(nthreads);  // s_tgt and the reduce scratch are reused by the caller's next segment

@@ -48,7 +48,7 @@ SIGNATURES = {
     "sd_verify_set_variant": (_i, [_i, _i]),
     "sd_verify_set_trace": (_i, [_vp, _sz]),
     "sd_kv_append": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp,
-                          _i, _vp, _i, _i64, _vp, _vp, _i, _vp]),
+                          _i, _vp, _i, _i64, _vp, _vp, _i, _vp, _vp, _vp]),
     "sd_kv_append_layer": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                                 _vp, _i, _vp, _i, _vp, _vp]),
     "sd_kv_set_variant": (_i, [_i]),

@@ -43,7 +43,11 @@ class VerifyStep:
         self.arena = arena
         self.mode, self.threshold, self.temperature = mode, threshold, temperature
         self.rows_ready_early = False
-        self.exchange = exchange  # scheduler.batch_shard.PeerExchange: records also go to every peer GPU
+        # scheduler.batch_shard.PeerExchange: the records also go to every peer GPU.  They are confirmed and
+        # gathered by the append launch when there is an arena, else by a wait kernel; set
+        # ``exchange_wait = False`` when the caller issues that step itself (bench.py appends separately).
+        self.exchange = exchange
+        self.exchange_wait = True
         dev = self.device
         self.logits = torch.zeros((batch, k_draft + 1, vocab), dtype=logits_dtype, device=dev)
         self.draft_ids = torch.zeros((batch, k_draft), dtype=id_dtype, device=dev)
@@ -79,7 +83,10 @@ class VerifyStep:
             # rows_ready_early would be legal here; measured on B200 it buys nothing -- the verify CTAs
             # hold the registers until the very end -- and it reads the rejected rows too)
             self.arena.append(self.accept_len, keep_bias=1, zero_rejected=True, check_capacity=False,
-                              rows_ready_early=self.rows_ready_early)
+                              rows_ready_early=self.rows_ready_early,
+                              exchange=self.exchange if self.exchange_wait else None)
+        elif self.exchange is not None and self.exchange_wait:
+            self.exchange.wait()
 
     # -- CUDA graph (reference: src/specdec/utils/graph_capture.py:49-99 GraphCapture, never wired in) --
     def capture(self) -> None:

@@ -109,6 +109,8 @@ def test_peer_exchange_emulated_ranks(world, global_batch):
     xs = PeerExchange.emulate(world, global_batch, K, "cuda")
     try:
         steps = [VerifyStep(x.shard.local_batch, K, V, exchange=x) for x in xs]
+        for st in steps:
+            st.exchange_wait = False  # every rank's verify must be launched before any rank waits
         for it in range(5):
             logits, ids = make_verify_inputs(global_batch, K + 1, K, V, "bf16", p_match=0.6, seed=100 + it, device="cuda")
             e_acc, _, e_tgt, _ = c_oracle.verify(to_np(logits), "bf16", to_np(ids))
@@ -123,6 +125,47 @@ def test_peer_exchange_emulated_ranks(world, global_batch):
             torch.cuda.synchronize()
             for r, got in enumerate(gathered):
                 np.testing.assert_array_equal(got.cpu().numpy(), want, err_msg=f"rank {r} step {it}")
+    finally:
+        for x in xs:
+            x.close()
+
+
+def test_peer_exchange_gathered_by_the_append_launch():
+    """Same exchange, but confirmed + gathered by the last CTA of kv_append (no wait launch): the table
+    lands in exchange.out, epochs advance, KV and lengths stay bit-exact."""
+    from scheduler.batch_shard import PeerExchange
+
+    world, K, V, layers, H, D, L, cap = 2, 4, 2053, 2, 2, 64, 5, 64
+    global_batch = 6
+    xs = PeerExchange.emulate(world, global_batch, K, "cuda")
+    try:
+        arenas, steps = [], []
+        for x in xs:
+            n = x.shard.local_batch
+            a = KVArena(layers, n, H, D, cap, K + 1, torch.bfloat16, "cuda")
+            a.set_lengths([L] * n)
+            arenas.append(a)
+            st = VerifyStep(n, K, V, arena=None, exchange=x)  # the test issues the append itself
+            st.exchange_wait = False
+            steps.append(st)
+        lens = [np.full(x.shard.local_batch, L, np.int32) for x in xs]
+        for it in range(4):
+            logits, ids = make_verify_inputs(global_batch, K + 1, K, V, "bf16", p_match=0.7, seed=300 + it, device="cuda")
+            e_acc, _, e_tgt, _ = c_oracle.verify(to_np(logits), "bf16", to_np(ids))
+            want = O.pack_step_result(e_acc, e_tgt)
+            for x, st in zip(xs, steps):  # every rank's verify first (pushes the records) ...
+                s, e = x.shard.bounds()
+                st.logits.copy_(logits[s:e])
+                st.draft_ids.copy_(ids[s:e])
+                st.run()
+            for r, (x, st, a) in enumerate(zip(xs, steps, arenas)):  # ... then the appends, which gather
+                a.append(st.accept_len, keep_bias=1, exchange=x)
+                s, e = x.shard.bounds()
+                lens[r] = lens[r] + e_acc[s:e] + 1
+            torch.cuda.synchronize()
+            for r, (x, a) in enumerate(zip(xs, arenas)):
+                np.testing.assert_array_equal(x.unpad(x.out).cpu().numpy(), want, err_msg=f"rank {r} step {it}")
+                np.testing.assert_array_equal(a.seq_lens.cpu().numpy(), lens[r])
     finally:
         for x in xs:
             x.close()

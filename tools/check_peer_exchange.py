@@ -33,6 +33,7 @@ def main():
     peer = PeerExchange(shard, K, dev)
     nccl = StepResultExchange(shard, K, dev)
     st = VerifyStep(B, K, V, device=dev, exchange=peer)
+    st.exchange_wait = False  # this script issues peer.wait() / the fused append itself
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     bad = 0
     for it in range(6):
@@ -99,12 +100,48 @@ def main():
         st.exchange = None
         st.run()
 
+    from specdec.cache.kv_arena import KVArena
+
+    arena = KVArena(28, B, 8, 128, 1024 + 5 * 400, K + 1, torch.bfloat16, dev)
+    arena.set_lengths([1024] * B)
+    lens0 = torch.full((B,), 1024, dtype=torch.int32, device=dev)
+
+    def step_fused():  # verify (pushes records) -> kv_append (last CTA confirms + gathers)
+        st.exchange = peer
+        st.run()
+        arena.seq_lens.copy_(lens0)
+        arena.append(st.accept_len, keep_bias=1, check_capacity=False, exchange=peer)
+
+    def step_plain():
+        st.exchange = None
+        st.run()
+        arena.seq_lens.copy_(lens0)
+        arena.append(st.accept_len, keep_bias=1, check_capacity=False)
+
+    def step_plain_nccl():
+        step_plain()
+        nccl.all_gather(st.packed)
+
     t_peer, t_nccl, t_none = timed(step_peer), timed(step_nccl), timed(step_none)
+    t_fused, t_plain, t_plain_nccl = timed(step_fused), timed(step_plain), timed(step_plain_nccl)
+    # correctness of the fused path once more after the timing loops
+    st.exchange = peer
+    st.run()
+    arena.seq_lens.copy_(lens0)
+    arena.append(st.accept_len, keep_bias=1, check_capacity=False, exchange=peer)
+    got = peer.out.clone()
+    want = nccl.all_gather(st.packed).clone()
+    torch.cuda.synchronize()
+    if not torch.equal(got, want):
+        bad += 1
+        print(f"[rank {rank}] fused append: MISMATCH", flush=True)
     ok = torch.tensor([bad], device=dev)
     dist.all_reduce(ok)
     if rank == 0:
         print(json.dumps({"world": world, "mismatches": int(ok.item()), "verify_only_us": t_none,
-                          "verify_plus_peer_exchange_us": t_peer, "verify_plus_nccl_allgather_us": t_nccl}), flush=True)
+                          "verify_plus_peer_exchange_us": t_peer, "verify_plus_nccl_allgather_us": t_nccl,
+                          "step_verify_kv_us": t_plain, "step_with_fused_exchange_us": t_fused,
+                          "step_with_nccl_allgather_us": t_plain_nccl}), flush=True)
     torch.cuda.synchronize()
     sys.stdout.flush()
     os._exit(0 if int(ok.item()) == 0 else 1)
