@@ -99,20 +99,25 @@ def summarise_launches(csv_path: Path, round_name: str) -> Path:
     rows = list(csv.DictReader(io.StringIO(text[start:])))
     agg = defaultdict(list)
     order = []
+    other = "(torch setup kernels outside the timed region: fill / randn / copy / index)"
     for r in rows:
         k = r["Kernel Name"]
+        if "sd::" not in k:
+            r["Kernel Name"] = k = other
+            r["Grid Size"], r["Block Size"] = "-", "-"
         if k not in agg:
             order.append(k)
         agg[k].append(float(r["Metric Value"]) / 1e3)
-    total = sum(sum(v) for v in agg.values())
+    total = sum(sum(v) for k, v in agg.items() if k != other)
     lines = [f"# launch list {csv_path.name} ({round_name})", "",
              "`ncu --metrics gpu__time_duration.sum --clock-control none` over `bench.py`; per-launch times are cold-cache and "
              "serialised, so the SHARE column is the quantity to compare with the bench's event timings.", "",
-             "| kernel | launches | grid x block | mean us | min us | max us | share of listed GPU time |", "|---|---|---|---|---|---|---|"]
+             "| kernel | launches | grid x block | mean us | min us | max us | share of this library's GPU time |", "|---|---|---|---|---|---|---|"]
     geo = {r["Kernel Name"]: f'{r["Grid Size"]} x {r["Block Size"]}' for r in rows}
     for k in order:
         v = agg[k]
-        lines.append(f"| `{k}` | {len(v)} | {geo[k]} | {sum(v) / len(v):.2f} | {min(v):.2f} | {max(v):.2f} | {100 * sum(v) / total:.1f} % |")
+        share = "-" if k == other else f"{100 * sum(v) / total:.1f} %"
+        lines.append(f"| `{k}` | {len(v)} | {geo[k]} | {sum(v) / len(v):.2f} | {min(v):.2f} | {max(v):.2f} | {share} |")
     out = PROFILES / f"{round_name}_{csv_path.stem}.md"
     out.write_text("\n".join(lines) + "\n")
     return out
