@@ -48,8 +48,11 @@ enum sd_accept_mode {
     SD_ACCEPT_GREEDY = 0,     /* argmax == draft           reference: src/kernels/reference.py:37-54 */
     SD_ACCEPT_TYPICAL = 1,    /* softmax(target)[draft] >= threshold
                                  reference: src/specdec/policies/policies.py:358-373 */
-    SD_ACCEPT_CONFIDENCE = 2  /* max softmax(logits) >= threshold
+    SD_ACCEPT_CONFIDENCE = 2, /* max softmax(logits) >= threshold
                                  reference: src/specdec/policies/policies.py:240-250 */
+    SD_ACCEPT_TOPK = 3        /* draft token among the target's top-k: fewer than `threshold` (= k) logits
+                                 strictly above it; token_prob then returns that count, row_sumexp is
+                                 meaningless.  reference: src/specdec/policies/policies.py:300-314 */
 };
 
 int sd_abi_version(void);

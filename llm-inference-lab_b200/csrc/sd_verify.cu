@@ -144,7 +144,8 @@ struct ThreadAcc {
     uint32_t run;     // replicated scalar running max (packed)
     int first_it;     // vector index (within the row) where `run` first appeared
     uint4 bestv;      // that vector (the exact element is resolved from it at the end of the segment)
-    float sm, ss;     // STATS: reference max (log2 domain) and sum of 2^(x - sm)
+    float sm, ss;     // STATS: reference max (log2 domain) and sum of 2^(x - sm); top-k mode: sm = 0, ss = count
+    float xtok;       // STATS, top-k mode: logit of the draft token (count the elements above it); NaN = softmax mode
 
     SD_DEVINL void reset() {
         run = Packed<T>::kNegInf;
@@ -152,7 +153,15 @@ struct ThreadAcc {
         bestv = make_uint4(0u, 0u, 0u, 0u);
         sm = -INFINITY;
         ss = 0.f;
+        xtok = __uint_as_float(0x7fc00000u);
     }
+
+    // top-k agreement mode: count logits strictly above `x` instead of accumulating the softmax sum
+    SD_DEVINL void count_above(float x) {
+        xtok = x;
+        sm = 0.f;
+    }
+    SD_DEVINL bool counting() const { return xtok == xtok; }
 
     // fold one 16-byte vector (index `idx` in its row); `live` = the vector exists
     SD_DEVINL void add(const uint4& v, int idx, bool live, float scale_log2) {
@@ -166,6 +175,26 @@ struct ThreadAcc {
             bestv = v;
         }
         if constexpr (STATS) {
+            if (counting()) {
+                if (live) {
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if constexpr (sizeof(T) == 4) {
+                            ss += __uint_as_float(w[q]) > xtok ? 1.f : 0.f;
+                        } else if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                            ss += __uint_as_float(w[q] << 16) > xtok ? 1.f : 0.f;
+                            ss += __uint_as_float(w[q] & 0xffff0000u) > xtok ? 1.f : 0.f;
+                        } else {
+                            float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+                            ss += f.x > xtok ? 1.f : 0.f;
+                            ss += f.y > xtok ? 1.f : 0.f;
+                        }
+                    }
+                }
+                run = nw;
+                return;
+            }
             if (live && nw != run) {
                 float mn = P::scalar(nw) * scale_log2;
                 ss = (sm == -INFINITY) ? 0.f : ss * fast_exp2(sm - mn);
@@ -191,6 +220,16 @@ struct ThreadAcc {
         run = nw;
     }
 };
+
+// top-k agreement (policies.py:300-314): logit of the draft token of global row `row`, +inf for the
+// bonus row / an out-of-range id (nothing is above +inf -> count 0)
+template <typename T>
+SD_DEVINL float draft_logit(const VerifyParams& p, const RowGeom<T>& g, int row) {
+    const int b = row / p.rows, j = row - b * p.rows;
+    if (j >= p.K) return INFINITY;
+    const int tok = load_id(p.ids, p.id_dtype, (int64_t)b * p.id_stride_b + j);
+    return (tok >= 0 && tok < p.V) ? to_float<T>(g.base[tok]) : INFINITY;
+}
 
 // first maximal element of one 16-byte vector whose first element has row index `pos0`
 template <typename T>
@@ -267,8 +306,12 @@ SD_DEVINL bool publish_segment(const VerifyParams& p, const RowGeom<T>& g, Threa
             Cand c2{order_key(x), pos};
             c = better(c, c2);
             if constexpr (STATS) {
-                float xm = x * p.scale_log2;
-                merge_ms(sm, ss, xm, 1.f);
+                if (acc.counting()) {
+                    ss += x > acc.xtok ? 1.f : 0.f;
+                } else {
+                    float xm = x * p.scale_log2;
+                    merge_ms(sm, ss, xm, 1.f);
+                }
             }
         }
     }
@@ -403,6 +446,8 @@ SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int n
                 if (r < p.K) {
                     if (p.mode == SD_ACCEPT_CONFIDENCE) {
                         pt = 1.0f / fs;
+                    } else if (p.mode == SD_ACCEPT_TOPK) {
+                        pt = (tok >= 0 && tok < V) ? fs : INFINITY;  // logits strictly above the draft token's
                     } else if (tok >= 0 && tok < V) {
                         pt = fast_exp2(xtok * p.scale_log2 - fm) / fs;
                     }
@@ -420,7 +465,8 @@ SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int n
             const int k = h * 32 + lane;
             bool bad = false;
             if (k < p.K) {
-                if (STATS && p.mode != SD_ACCEPT_GREEDY) bad = !(s_ptok[k] >= p.threshold);
+                if (STATS && p.mode == SD_ACCEPT_TOPK) bad = !(s_ptok[k] < p.threshold);
+                else if (STATS && p.mode != SD_ACCEPT_GREEDY) bad = !(s_ptok[k] >= p.threshold);
                 else bad = s_tgt[k] != my_id[h];
             }
             const unsigned ballot = __ballot_sync(0xffffffffu, bad);
@@ -473,6 +519,9 @@ SD_DEVINL bool process_segment(const VerifyParams& p, const int row, const int i
     const RowGeom<T> g = row_geom<T>(p, row);
     ThreadAcc<T, STATS> acc;
     acc.reset();
+    if constexpr (STATS) {
+        if (p.mode == SD_ACCEPT_TOPK) acc.count_above(draft_logit<T>(p, g, row));
+    }
     for (int i0 = it0; i0 < it1; i0 += VPT) {
         uint4 buf[VPT];
 #pragma unroll
@@ -647,6 +696,9 @@ __global__ void __launch_bounds__(kTmaConsumers + 32) verify_tma_kernel(const Ve
         const RowGeom<T> g = row_geom<T>(p, row);
         ThreadAcc<T, STATS> acc;
         acc.reset();
+        if constexpr (STATS) {
+            if (p.mode == SD_ACCEPT_TOPK) acc.count_above(draft_logit<T>(p, g, row));
+        }
         for (int uu = u; uu < seg_end; ++uu) {
             const int v0 = (uu - row * p.upr) * UV;
             vbar_wait(&full_bar[s], ph);
@@ -715,9 +767,12 @@ __global__ void __launch_bounds__(256) verify_bulk_kernel(const VerifyParams p) 
             vbar_arrive(&bar);
         }
     }
-    vbar_wait(&bar, 0u);
     ThreadAcc<T, STATS> acc;
     acc.reset();
+    if constexpr (STATS) {  // overlaps the bulk copy
+        if (p.mode == SD_ACCEPT_TOPK) acc.count_above(draft_logit<T>(p, g, row));
+    }
+    vbar_wait(&bar, 0u);
     const uint4* src = reinterpret_cast<const uint4*>(stage);
 #pragma unroll 4
     for (int k = tid; k < nv; k += nthreads) acc.add(src[k], v0 + k, true, p.scale_log2);
@@ -838,7 +893,7 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
     if (!logits || !accept_len || (K > 0 && !draft_ids)) return SD_ERR_INVALID_ARG;
     if (logit_dtype < SD_F32 || logit_dtype > SD_BF16 || (id_dtype != SD_I32 && id_dtype != SD_I64))
         return SD_ERR_INVALID_ARG;
-    if (mode < SD_ACCEPT_GREEDY || mode > SD_ACCEPT_CONFIDENCE) return SD_ERR_INVALID_ARG;
+    if (mode < SD_ACCEPT_GREEDY || mode > SD_ACCEPT_TOPK) return SD_ERR_INVALID_ARG;
     const int es = elt_size(logit_dtype);
     if (reinterpret_cast<uintptr_t>(logits) % es || reinterpret_cast<uintptr_t>(workspace) % 8) return SD_ERR_ALIGNMENT;
     WorkspaceLayout w = layout(B, rows);

@@ -17,7 +17,7 @@ from . import build as _build
 
 DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
 ID_I32, ID_I64 = 0, 1
-ACCEPT_GREEDY, ACCEPT_TYPICAL, ACCEPT_CONFIDENCE = 0, 1, 2
+ACCEPT_GREEDY, ACCEPT_TYPICAL, ACCEPT_CONFIDENCE, ACCEPT_TOPK = 0, 1, 2, 3
 ABI_VERSION = 2
 
 _vp = C.c_void_p

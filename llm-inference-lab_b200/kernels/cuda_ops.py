@@ -24,7 +24,8 @@ from . import _capi
 _DTYPE = {torch.float32: _capi.DTYPE_F32, torch.float16: _capi.DTYPE_F16, torch.bfloat16: _capi.DTYPE_BF16}
 _ID_DTYPE = {torch.int32: _capi.ID_I32, torch.int64: _capi.ID_I64}
 
-ACCEPT_MODES = {"greedy": _capi.ACCEPT_GREEDY, "typical": _capi.ACCEPT_TYPICAL, "confidence": _capi.ACCEPT_CONFIDENCE}
+ACCEPT_MODES = {"greedy": _capi.ACCEPT_GREEDY, "typical": _capi.ACCEPT_TYPICAL, "confidence": _capi.ACCEPT_CONFIDENCE,
+                "topk": _capi.ACCEPT_TOPK}
 
 
 def _require_cuda(t: torch.Tensor, what: str) -> None:
@@ -214,6 +215,8 @@ def verify_step_cuda(
 
     mode "typical":    accept while softmax(target)[draft] >= threshold (policies.py:358-373)
     mode "confidence": accept while max softmax(logits) >= threshold     (policies.py:240-250)
+    mode "topk":       accept while fewer than ``threshold`` (= k) target logits lie strictly above the
+                       draft token's (policies.py:300-314); ``token_prob`` then holds that count
     mode "greedy":     argmax match, statistics still returned
     logits [B,K or K+1,V].  Returns dict(accept_len, accepted_mask, target_ids, bonus, token_prob,
     row_max, row_sumexp)."""
