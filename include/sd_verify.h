@@ -293,6 +293,31 @@ int sd_verify_attention(const void* q, const void* k_arena, const void* v_arena,
                         int64_t kv_stride_b, int64_t kv_stride_h, int64_t max_seq_len_host,
                         float scale, int n_splits, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Kernel 4: batched bonus-token sampler.
+ *
+ * Replaces  sample_bonus_token_from_logits(logits[V], temperature, do_sample, top_p, top_k)
+ *           reference: src/specdec/core/pipeline.py:48-147, called once per sequence at
+ *           :3140-3163 / :3174-3206 / :3341-3362 on logits row accept_len[b].
+ * for the whole batch in one launch (one CTA per sequence, no sort: radix select by count for top-k
+ * and by probability mass for top-p, fixed-point masses -> deterministic).
+ *
+ * logits     [B, rows, V], element strides (stride_b, stride_r, 1)
+ * row_index  [B] int32 (nullable): row = clamp(row_index[b] + row_bias, 0, rows-1); NULL -> row_const.
+ *            Typically the accept_len written by sd_verify_* on the same stream (row_bias = 0).
+ * uniform    [B] float in [0,1) (nullable).  NULL = greedy branch (pipeline.py:135-137): argmax.
+ *            Otherwise token = first index t (index order) whose cumulative probability over the
+ *            filtered distribution exceeds uniform[b]: the distribution is the reference's
+ *            (temperature :91-92, top-k :95-102, top-p :105-121 with "keep at least one"); its
+ *            torch.multinomial draw depends on torch's RNG stream and cannot be reproduced.
+ * top_k      <= 0 = off;  top_p >= 1 (or <= 0) = off;  temperature > 0 when sampling
+ * kept_count [B] int32 (nullable): size of the final candidate set
+ */
+int sd_sample_bonus(const void* logits, int logit_dtype, int64_t stride_b, int64_t stride_r,
+                    const int32_t* row_index, int row_bias, int row_const, const float* uniform,
+                    float temperature, int top_k, float top_p, int32_t* out_tokens,
+                    int32_t* kept_count, int B, int rows, int V, void* stream);
+
 /* Tile configuration of the attention kernel (evidence runs): 0 = heuristic, 1 = 16-key tiles x 3
  * stages (two CTAs per SM at D = 128), 2 = 32-key tiles x 3 (4 at D = 64) stages, 3 = 32-key x 2. */
 int sd_verify_attention_set_tuning(int config);

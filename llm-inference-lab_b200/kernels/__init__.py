@@ -14,6 +14,7 @@ What is registered (all device "cuda", priority 100, function names containing "
   verify_step          -> cuda_ops.verify_step_cuda            (softmax-mode acceptance)
   kv_append_with_mask  -> cuda_ops.kv_append_with_mask_cuda    (reference.py:96-159 semantics)
   verify_attention     -> cuda_ops.verify_attention_cuda       ((K+1)-query decode attention)
+  sample_bonus         -> cuda_ops.sample_bonus_cuda           (batched bonus-token sampler, pipeline.py:48-147)
 
 There is no Triton entry, no PyTorch entry and no CPU entry: on a CPU-only host ``get_best``
 returns None for every op (the reference's callers already handle ``None``:
@@ -42,6 +43,7 @@ _OPS = {
     "verify_step": cuda_ops.verify_step_cuda,
     "kv_append_with_mask": cuda_ops.kv_append_with_mask_cuda,
     "verify_attention": cuda_ops.verify_attention_cuda,
+    "sample_bonus": cuda_ops.sample_bonus_cuda,
 }
 
 # Build (nvcc, sm_100a) if stale and dlopen the C-ABI library.  Errors propagate.

@@ -246,6 +246,59 @@ def verify_step_cuda(
     return out
 
 
+# ------------------------------------------------------------------------------------------ bonus sampler
+def sample_bonus_cuda(
+    logits: torch.Tensor,
+    row_index: Optional[torch.Tensor] = None,
+    uniform: Optional[torch.Tensor] = None,
+    temperature: float = 1.0,
+    top_k: Optional[int] = None,
+    top_p: Optional[float] = None,
+    row: int = 0,
+    row_bias: int = 0,
+    out: Optional[torch.Tensor] = None,
+    kept_count: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """Batched ``sample_bonus_token_from_logits`` (reference: src/specdec/core/pipeline.py:48-147; new
+    registry op ``sample_bonus``).
+
+    logits [B, rows, V] (or [B, V]); ``row_index`` [B] int32 on device selects the row per sequence
+    (typically the ``accept_len`` the verify kernel wrote), else ``row``.  ``uniform`` [B] float32 in [0,1)
+    drives the draw (``do_sample=True``); ``None`` is the greedy branch.  Returns tokens [B] int32.  One
+    launch, no sort, no host sync."""
+    if logits.dim() == 2:
+        logits = logits.unsqueeze(1)
+    assert logits.dim() == 3, "logits must be [B, rows, V] or [B, V]"
+    _require_cuda(logits, "logits")
+    if logits.dtype not in _DTYPE:
+        raise TypeError(f"logits dtype {logits.dtype} not supported")
+    if logits.stride(2) != 1:
+        logits = logits.contiguous()
+    B, rows, V = logits.shape
+    dev = logits.device
+    if out is None:
+        out = torch.empty(B, dtype=torch.int32, device=dev)
+    if B == 0:
+        return out
+    if uniform is not None:
+        if temperature <= 0:
+            raise ValueError("temperature must be > 0 when sampling")
+        uniform = uniform.to(device=dev, dtype=torch.float32).contiguous()
+        assert uniform.numel() == B
+    if row_index is not None:
+        row_index = row_index.to(device=dev, dtype=torch.int32).contiguous()
+        assert row_index.numel() == B
+    lib = _capi.lib()
+    with torch.cuda.device(dev):
+        rc = lib.sd_sample_bonus(
+            logits.data_ptr(), _DTYPE[logits.dtype], logits.stride(0), logits.stride(1), _ptr(row_index), row_bias, row,
+            _ptr(uniform), float(temperature), int(top_k or 0), float(top_p if top_p is not None else 1.0),
+            out.data_ptr(), _ptr(kept_count), B, rows, V, _stream_ptr(dev),
+        )
+    lib.check(rc, "sd_sample_bonus")
+    return out
+
+
 # ------------------------------------------------------------------------------------------ kv append
 class _ArenaTag:
     """Attached (attribute ``_sd_arena``) to the [B,H,C,D] buffer behind tensors returned by

@@ -169,3 +169,32 @@ def test_peer_exchange_gathered_by_the_append_launch():
     finally:
         for x in xs:
             x.close()
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_sampled_bonus_in_the_step(use_graph):
+    """do_sample=True: the bonus token of row accept_len[b] is drawn on the device in the same step
+    (reference defaults: temperature 0.7, top_k 50, top_p 0.9 -- pipeline.py:405-410)."""
+    B, K, V = 6, 4, 32000
+    step = VerifyStep(B, K, V, bonus_sampling=dict(temperature=0.7, top_k=50, top_p=0.9))
+    logits, ids = make_verify_inputs(B, K + 1, K, V, "bf16", p_match=0.6, seed=21, device="cuda")
+    step.logits.copy_(logits)
+    step.draft_ids.copy_(ids)
+    if use_graph:
+        step.capture()
+    for it in range(3):
+        step.uniform.copy_(torch.rand(B, generator=torch.Generator().manual_seed(it)))
+        step.replay() if use_graph else step.run()
+        torch.cuda.synchronize()
+        acc, _, tgt, _ = c_oracle.verify(to_np(logits), "bf16", to_np(ids))
+        np.testing.assert_array_equal(step.accept_len.cpu().numpy(), acc)
+        x = O.as_f32(to_np(logits), "bf16")
+        u = step.uniform.cpu().numpy()
+        for b in range(B):
+            row = x[b, acc[b]]
+            filt = O.bonus_logits_filter(row, 0.7, 50, 0.9)
+            _, cdf = O.sample_bonus(row, 0.7, 50, 0.9, float(u[b]))
+            t = int(step.bonus[b])
+            assert np.isfinite(filt[t])
+            lo = cdf[t - 1] if t > 0 else 0.0
+            assert lo - 2e-5 <= u[b] < cdf[t] + 2e-5
