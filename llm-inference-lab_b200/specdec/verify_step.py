@@ -37,6 +37,7 @@ class VerifyStep:
         threshold: float = 0.0,
         temperature: float = 1.0,
         exchange=None,
+        bonus_sampling: Optional[dict] = None,
     ) -> None:
         self.B, self.K, self.V = batch, k_draft, vocab
         self.device = torch.device(device)
@@ -48,6 +49,11 @@ class VerifyStep:
         # ``exchange_wait = False`` when the caller issues that step itself (bench.py appends separately).
         self.exchange = exchange
         self.exchange_wait = True
+        # do_sample=True bonus tokens (reference: pipeline.py:48-147): dict(temperature=, top_k=, top_p=).  The
+        # draw uses ``self.uniform`` [B] in [0,1) -- refill it (``step.uniform.uniform_()``) before every step;
+        # ``self.bonus`` then holds the SAMPLED token of row accept_len[b] (``packed`` keeps the greedy ids).
+        self.bonus_sampling = bonus_sampling
+        self.uniform = torch.rand(batch, dtype=torch.float32, device=dev) if bonus_sampling else None
         dev = self.device
         self.logits = torch.zeros((batch, k_draft + 1, vocab), dtype=logits_dtype, device=dev)
         self.draft_ids = torch.zeros((batch, k_draft), dtype=id_dtype, device=dev)
@@ -62,7 +68,7 @@ class VerifyStep:
         need = int(_capi.lib().sd_verify_workspace_bytes(batch, k_draft + 1))
         self.workspace = torch.zeros(need, dtype=torch.uint8, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        self.launches_per_step = 1 + (1 if arena is not None else 0)
+        self.launches_per_step = 1 + (1 if arena is not None else 0) + (1 if bonus_sampling else 0)
 
     # -- eager ------------------------------------------------------------------------------------
     def run(self, logits: Optional[torch.Tensor] = None, draft_ids: Optional[torch.Tensor] = None) -> None:
@@ -77,6 +83,10 @@ class VerifyStep:
             stats=self.mode != "greedy",
             exchange=self.exchange.desc_ptr if self.exchange is not None else None,
         )
+        if self.bonus_sampling is not None:
+            cuda_ops.sample_bonus_cuda(lg, row_index=self.accept_len, uniform=self.uniform, out=self.bonus,
+                                       temperature=self.bonus_sampling.get("temperature", 1.0),
+                                       top_k=self.bonus_sampling.get("top_k"), top_p=self.bonus_sampling.get("top_p"))
         if self.arena is not None:
             # keep accept_len drafts + the token they were conditioned on (row 0 of the pass)
             # (the staged K/V rows come from the target forward, i.e. from before the verify launch, so
