@@ -53,8 +53,8 @@ class VerifyStep:
         # draw uses ``self.uniform`` [B] in [0,1) -- refill it (``step.uniform.uniform_()``) before every step;
         # ``self.bonus`` then holds the SAMPLED token of row accept_len[b] (``packed`` keeps the greedy ids).
         self.bonus_sampling = bonus_sampling
-        self.uniform = torch.rand(batch, dtype=torch.float32, device=dev) if bonus_sampling else None
         dev = self.device
+        self.uniform = torch.rand(batch, dtype=torch.float32, device=dev) if bonus_sampling else None
         self.logits = torch.zeros((batch, k_draft + 1, vocab), dtype=logits_dtype, device=dev)
         self.draft_ids = torch.zeros((batch, k_draft), dtype=id_dtype, device=dev)
         self.accept_len = torch.zeros(batch, dtype=torch.int32, device=dev)
