@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--tuning", default="", help="threads,vectors_per_thread for the verify kernel (sweeps)")
     ap.add_argument("--kv-variant", type=int, default=0)
     ap.add_argument("--batch", type=int, default=CFG["B"], help="sequences per GPU")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--exchange", default="peer-kv", choices=["peer-kv", "peer", "nccl"],
                     help="N>1: fused peer-memory exchange in the verify kernel (default) or one NCCL all-gather per step")
     return ap.parse_args()
 
@@ -254,10 +254,11 @@ def run_ours(args):
     exch = peer = None
     exchange_kind = "none"
     if world > 1:
-        if args.exchange == "peer":
+        if args.exchange in ("peer", "peer-kv"):
             try:
                 peer = PeerExchange(shard, K, dev)
-                exchange_kind = "peer-memory stores from the verify kernel, confirmed + gathered by the last CTA of kv_append"
+                exchange_kind = ("peer-memory stores issued by the first CTA of kv_append, gathered by its last CTA" if args.exchange == "peer-kv"
+                                 else "peer-memory stores from the verify kernel, confirmed + gathered by the last CTA of kv_append")
             except Exception as e:  # noqa: BLE001  (CUDA IPC unavailable in this container)
                 print(f"[rank {rank}] PeerExchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr, flush=True)
         ok = torch.tensor([1 if peer is not None else 0], device=dev)
@@ -281,13 +282,18 @@ def run_ours(args):
         stage_k.append(torch.randn(arena.new_k.shape, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16))
         stage_v.append(torch.randn(arena.new_v.shape, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16))
     tables = [arena._build_table(stage_k[i], stage_v[i]) for i in range(NB)]
-    def one_step(i):
+    def one_step(i, px=None):
+        px = peer if px is None else px
         st = steps[i]
+        push_in_kv = args.exchange == "peer-kv"
+        st.exchange = None if push_in_kv else px
         st.run()
         arena.layer_table = tables[i]
-        # N>1, peer exchange: the last CTA of the append confirms + gathers the records the verify kernel
-        # pushed to every rank (no launch of its own)
-        arena.append(st.accept_len, keep_bias=1, zero_rejected=True, check_capacity=False, exchange=peer)
+        # N>1, peer exchange: the records are pushed to every rank by the verify finalizers ("peer") or by the
+        # first CTA of the append ("peer-kv": the NVLink round trip hides behind the append); the last CTA of
+        # the append confirms + gathers them (no launch of its own)
+        arena.append(st.accept_len, keep_bias=1, zero_rejected=True, check_capacity=False, exchange=px,
+                     exchange_packed=st.packed if (push_in_kv and px is not None) else None)
         if exch is not None:
             exch.all_gather(st.packed)
 
@@ -344,6 +350,23 @@ def run_ours(args):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     step_ms = ev0.elapsed_time(ev1) / args.steps
+
+    # N>1: the same loop with the PIPELINED exchange (lag 1: a step gathers the previous step's records, so
+    # the ranks are not forced into lockstep).  Reported next to the headline, which keeps lag 0.
+    lag1_ms = 0.0
+    if peer is not None:
+        peer1 = PeerExchange(shard, K, dev, lag=1)
+        run_lag1 = make_runner(lambda i: one_step(i, peer1))
+        run_lag1(args.warmup)
+        barrier()
+        a1, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a1.record()
+        run_lag1(args.steps)
+        b1.record()
+        barrier()
+        lag1_ms = a1.elapsed_time(b1) / args.steps
+        for st in steps:
+            st.exchange = peer
 
     # ---- kernel-isolation loops for the roofline (same buffers, same rotation, CUDA events) ----
     def isolate(fn_of_i, n_launch):
@@ -424,9 +447,9 @@ def run_ours(args):
 
     # ---- reduce over ranks: max time, summed tokens ----
     if world > 1:
-        t = torch.tensor([step_ms, verify_ms, kv_ms, attn_ms, e2e["seconds"] if e2e else 0.0], device=dev, dtype=torch.float64)
+        t = torch.tensor([step_ms, verify_ms, kv_ms, attn_ms, e2e["seconds"] if e2e else 0.0, lag1_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms, verify_ms, kv_ms, attn_ms, e2e_s = (float(x) for x in t.tolist())
+        step_ms, verify_ms, kv_ms, attn_ms, e2e_s, lag1_ms = (float(x) for x in t.tolist())
         c = torch.tensor([tokens_per_step, float(e2e["tokens"]) if e2e else 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         tokens_per_step_all, e2e_tokens_all = (float(x) for x in c.tolist())
@@ -456,6 +479,9 @@ def run_ours(args):
             "launches_per_step": {"sd_verify_kernel": 1, "sd_kv_append_kernel": 1,
                                   "nccl_allgather": 1 if exch is not None else 0},
             "exchange": exchange_kind,
+            "pipelined_exchange": ({"lag_steps": 1, "ms_per_step": lag1_ms, "value": tokens_per_step_all / (lag1_ms * 1e-3),
+                                    "note": "same step, but each append gathers the PREVIOUS step's records: ranks are not in lockstep; "
+                                            "every rank still has its own shard's records immediately"} if lag1_ms > 0 else None),
             "roofline": {"bound": "hbm", "kernel": "verify_bulk_kernel<bf16> (one cp.async.bulk per CTA chunk)", "achieved": v_gbs, "peak": peak, "unit": "GB/s",
                          "frac": v_gbs / peak, "frac_of_8TBs_nominal": v_gbs / 8000.0, "traffic": traffic.get("verify_bulk_kernel"),
                          "algorithmic_bytes": verify_bytes, "us_per_launch": verify_ms * 1e3, "peak_source": peak_src},

@@ -74,11 +74,11 @@ int sd_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * travels in ONE 8-byte store together with an epoch tag -- {epoch + 1, value} -- so the data path needs
  * no fence, atomic or arrival counter: the consumer (the last CTA of sd_kv_append, or
  * sd_exchange_wait) polls the words of the current epoch until their tags match, copies the values
- * out and advances the device-side epoch.  Words are double buffered by epoch parity: a rank can be
- * at most one step ahead of its slowest peer.
+ * out and advances the device-side epoch.  Words live in 4 slots indexed by epoch & 3, which covers
+ * lag <= 1 (a producer is never more than two epochs ahead of a slot still being read).
  *
  * Exchange buffer (identical on every rank, sd_exchange_bytes): 256-byte header {u32 epoch} +
- * u64 words[2][world * rows_per_rank][width].  The descriptor lives in DEVICE memory; peer[rank] is the
+ * u64 words[4][world * rows_per_rank][width].  The descriptor lives in DEVICE memory; peer[rank] is the
  * rank's own buffer.  Rank r holds total_rows / world (+1 for the first total_rows % world ranks) rows.
  */
 #define SD_MAX_PEERS 16
@@ -87,7 +87,9 @@ typedef struct sd_exchange {
     int32_t rows_per_rank; /* record rows reserved per rank (max local batch) */
     int32_t width;         /* K + 2 */
     int32_t total_rows;    /* sum of the local batches of all ranks = records arriving per step */
-    int32_t reserved[3];
+    int32_t lag;           /* 0: a step gathers its own records (ranks in lockstep); 1: the previous step's
+                              (a rank may run one step ahead of the slowest; the table lags one step) */
+    int32_t reserved[2];
     void* peer[SD_MAX_PEERS];
 } sd_exchange;
 
@@ -218,11 +220,15 @@ typedef struct sd_kv_layer {
  *             *overflow_flag (nullable, int32) is set non-zero.
  * ticket      one int32 in device memory, zero before the first launch (the kernel re-zeroes it).
  * exchange / exchange_out  (nullable) multi-GPU step: the records that the verify launch of this step
- *             pushed into every rank's exchange buffer are confirmed and gathered HERE, by the last
- *             CTA to retire (arrival count of the current epoch reached -> copy the
+ *             pushed into every rank's exchange buffer are gathered HERE, by the first CTA once its own
+ *             rows are copied (poll the tagged words of the epoch -> copy the
  *             [world * rows_per_rank, width] table to exchange_out -> advance the epoch), so the
  *             exchange hides behind the append and needs no launch of its own.  Use this INSTEAD of
  *             sd_exchange_wait for that step.
+ * exchange_packed  (nullable) [B, K+2] int32 packed records of THIS rank, complete before this launch
+ *             (written by the verify launch): when set, the first CTA of this launch pushes them to
+ *             every peer at its start -- the NVLink round trip then hides behind the append -- and
+ *             the verify launch must be issued WITHOUT `exchange`.
  * rows_ready_early  non-zero = the caller guarantees that the layer table and the offered rows were
  *             written at least two kernels before this call on the stream (in the verify step they
  *             come from the target forward; the kernel just before this one is the fused verify,
@@ -239,7 +245,8 @@ int sd_kv_append(const sd_kv_layer* layers, int n_layers, int B, int H, int R, i
                  const int32_t* seq_lens, int32_t* seq_lens_out, const int32_t* n_keep,
                  int keep_bias, const uint8_t* accepted_mask, int zero_rejected,
                  int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, int rows_ready_early,
-                 void* stream, const sd_exchange* exchange, int32_t* exchange_out);
+                 void* stream, const sd_exchange* exchange, int32_t* exchange_out,
+                 const int32_t* exchange_packed);
 
 /*
  * Single-layer form with the layer record passed by value and a uniform current length

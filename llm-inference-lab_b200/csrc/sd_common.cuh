@@ -165,33 +165,75 @@ SD_DEVINL int load_id(const void* ids, int id_dtype, int64_t i) {
 }
 
 // ---- peer-memory result exchange, consumer side (include/sd_verify.h: sd_exchange) ----
-// Exchange buffer: 256-byte header {u32 epoch} + u64 words[2][world * rows_per_rank][width], each word
-// {epoch + 1, value} written by ONE 8-byte store of the producing verify kernel.  Called by a whole CTA:
-// polls every expected word of the current epoch until its tag matches, writes the values to `out`
-// ([world * rows_per_rank, width] int32, nullable; rows beyond a rank's batch are left untouched), then
-// advances the epoch.  Rank r holds total_rows / world (+1 for the first total_rows % world ranks) rows.
+// Exchange buffer: 256-byte header {u32 epoch} + u64 words[4][world * rows_per_rank][width], each word
+// {epoch + 1, value} written by ONE 8-byte store of the producing verify kernel into slot epoch & 3.
+// Called by a whole CTA: gathers the records of epoch (current - lag) -- polls every expected word until
+// its tag matches, writes the values to `out` ([world * rows_per_rank, width] int32, nullable; rows
+// beyond a rank's batch are left untouched) -- then advances the epoch.  lag = 0: the step's own
+// records (all ranks run in lockstep); lag = 1: the previous step's (a rank may run one step ahead of
+// the slowest; nothing is gathered at epoch 0).  4 slots cover lag <= 1: a producer is never more
+// than 2 epochs ahead of a slot that is still being read.
+// Rank r holds total_rows / world (+1 for the first total_rows % world ranks) rows.
 constexpr int kExchangeHeaderBytes = 256;
+constexpr int kExchangeSlots = 4;
+// Producer side when the records are pushed by a kernel other than the verify kernel: one CTA stores the
+// `rows` local records packed[rows][width] (int32, already complete in local memory) into every rank's
+// slot of the current epoch, one tagged 8-byte word per value.
+SD_DEVINL void exchange_push_cta(const sd_exchange* x, const int32_t* packed, int rows) {
+    char* own = reinterpret_cast<char*>(x->peer[x->rank]);
+    unsigned epoch;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(epoch) : "l"(own) : "memory");
+    const unsigned long long tag = (unsigned long long)(epoch + 1u) << 32;
+    const int world = x->world, rpr = x->rows_per_rank, width = x->width;
+    const size_t slot_base = ((size_t)(epoch & 3u) * world + x->rank) * rpr * width;
+    const int n = rows * width;
+    for (int i = threadIdx.x; i < n * world; i += blockDim.x) {
+        const int pr = i / n, j = i - pr * n;
+        unsigned long long* recs = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(x->peer[pr]) + 256);
+        recs[slot_base + j] = tag | (unsigned)packed[j];
+    }
+}
+
 SD_DEVINL void exchange_gather_cta(const sd_exchange* x, int32_t* out) {
     char* own = reinterpret_cast<char*>(x->peer[x->rank]);
     unsigned epoch;
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(epoch) : "l"(own) : "memory");
-    const unsigned want = epoch + 1u;
-    const int world = x->world, rpr = x->rows_per_rank, width = x->width;
-    const int base = x->total_rows / world, extra = x->total_rows % world;
-    const unsigned long long* words =
-        reinterpret_cast<const unsigned long long*>(own + kExchangeHeaderBytes) + (size_t)(epoch & 1u) * world * rpr * width;
-    const int n = world * rpr * width;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int row = i / width;
-        const int r = row / rpr;
-        if (row - r * rpr >= base + (r < extra ? 1 : 0)) continue;  // padding row of an uneven shard
-        unsigned long long w;
-        for (;;) {
-            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(words + i) : "memory");
-            if ((unsigned)(w >> 32) == want) break;
-            __nanosleep(64);
+    const unsigned lag = (unsigned)x->lag;
+    if (epoch >= lag) {
+        const unsigned src = epoch - lag;
+        const unsigned want = src + 1u;
+        const int world = x->world, rpr = x->rows_per_rank, width = x->width;
+        const int base = x->total_rows / world, extra = x->total_rows % world;
+        const unsigned long long* words =
+            reinterpret_cast<const unsigned long long*>(own + kExchangeHeaderBytes) + (size_t)(src & 3u) * world * rpr * width;
+        const int n = world * rpr * width;
+        // Batches of kU words per thread: all loads of a batch are issued before the first tag check (one L2
+        // round trip per batch instead of one per word -- at world = 8 a thread owns 12 words); a word whose
+        // tag is stale is re-polled on its own.
+        constexpr int kU = 6;
+        for (int i0 = threadIdx.x; i0 < n; i0 += blockDim.x * kU) {
+            unsigned long long w[kU];
+            bool live[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int i = i0 + u * blockDim.x;
+                const int row = i / width;
+                const int r = row / rpr;
+                live[u] = i < n && (row - r * rpr) < base + (r < extra ? 1 : 0);  // not a padding row of an uneven shard
+                w[u] = 0ull;
+                if (live[u]) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w[u]) : "l"(words + i) : "memory");
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (!live[u]) continue;
+                const int i = i0 + u * blockDim.x;
+                while ((unsigned)(w[u] >> 32) != want) {
+                    __nanosleep(64);
+                    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w[u]) : "l"(words + i) : "memory");
+                }
+                if (out) out[i] = (int)(unsigned)w[u];
+            }
         }
-        if (out) out[i] = (int)(unsigned)w;
     }
     __syncthreads();
     if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(own) = epoch + 1u;

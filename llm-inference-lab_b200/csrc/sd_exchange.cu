@@ -18,7 +18,7 @@ extern "C" {
 
 size_t sd_exchange_bytes(int world, int rows_per_rank, int width) {
     if (world <= 0 || rows_per_rank <= 0 || width <= 0) return 0;
-    return (size_t)sd::kExchangeHeaderBytes + (size_t)2 * world * rows_per_rank * width * sizeof(unsigned long long);
+    return (size_t)sd::kExchangeHeaderBytes + (size_t)sd::kExchangeSlots * world * rows_per_rank * width * sizeof(unsigned long long);
 }
 
 int sd_exchange_alloc(size_t bytes, void** ptr_out, void* handle_out) {

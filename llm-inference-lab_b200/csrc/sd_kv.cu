@@ -40,6 +40,7 @@ struct KvParams {
     int32_t* ticket;
     const sd_exchange* xchg;  // nullable: confirm + gather the verify records of this step (last CTA)
     int32_t* xchg_out;
+    const int32_t* xchg_packed;  // nullable: this launch also PUSHES the local records (first CTA, at its start)
     unsigned total_ctas;
 };
 
@@ -90,10 +91,6 @@ SD_DEVINL void retire_and_commit(const KvParams& p) {
             p.seq_lens_out[b] = len + n;
         }
     }
-    // Fused result exchange (multi-GPU): the records the verify kernel pushed to every rank have had
-    // this whole kernel's duration to arrive; the last CTA polls the tagged words of the current epoch,
-    // copies the gathered table out and advances the epoch -- no separate wait launch.
-    if (p.xchg) exchange_gather_cta(p.xchg, p.xchg_out);
     __syncthreads();
     if (threadIdx.x == 0) *p.ticket = 0;
 }
@@ -102,6 +99,7 @@ template <typename VecT>
 __global__ void __launch_bounds__(256) kv_append_vec_kernel(const KvParams p) {
     pdl_wait();
     pdl_trigger();
+    if (p.xchg && p.xchg_packed && blockIdx.x == 0 && blockIdx.y == 0) exchange_push_cta(p.xchg, p.xchg_packed, p.B);
     const int layer = blockIdx.y;
     const int vpr = (int)(p.row_bytes / (int64_t)sizeof(VecT));
     const int64_t slots = (int64_t)p.B * p.H * p.R * vpr;
@@ -148,6 +146,10 @@ __global__ void __launch_bounds__(256) kv_append_vec_kernel(const KvParams p) {
             *p.overflow = 1;
         }
     }
+    // Fused result exchange (multi-GPU): CTA (0,0) -- which pushed this rank's records at its start when
+    // exchange_packed is set -- gathers every rank's records of the epoch once its own rows are copied:
+    // the NVLink round trips overlap the rest of the append instead of trailing it.
+    if (p.xchg && blockIdx.x == 0 && blockIdx.y == 0) exchange_gather_cta(p.xchg, p.xchg_out);
     retire_and_commit(p);
 }
 
@@ -188,6 +190,7 @@ __global__ void __launch_bounds__(256) kv_append_col_kernel(const KvParams p) {
     }
     pdl_wait();
     pdl_trigger();
+    if (p.xchg && p.xchg_packed && blockIdx.x == 0 && blockIdx.y == 0) exchange_push_cta(p.xchg, p.xchg_packed, p.B);
     if (active) {
         if (!p.early_rows) {
             v = (int)(slot % vpr);
@@ -232,6 +235,10 @@ __global__ void __launch_bounds__(256) kv_append_col_kernel(const KvParams p) {
             }
         }
     }
+    // Fused result exchange (multi-GPU): CTA (0,0) -- which pushed this rank's records at its start when
+    // exchange_packed is set -- gathers every rank's records of the epoch once its own rows are copied:
+    // the NVLink round trips overlap the rest of the append instead of trailing it.
+    if (p.xchg && blockIdx.x == 0 && blockIdx.y == 0) exchange_gather_cta(p.xchg, p.xchg_out);
     retire_and_commit(p);
 }
 
@@ -274,6 +281,7 @@ SD_DEVINL void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
 __global__ void __launch_bounds__(128) kv_append_bulk_kernel(const KvParams p) {
     pdl_wait();
     pdl_trigger();
+    if (p.xchg && p.xchg_packed && blockIdx.x == 0 && blockIdx.y == 0) exchange_push_cta(p.xchg, p.xchg_packed, p.B);
     extern __shared__ __align__(128) unsigned char stage[];
     __shared__ __align__(8) uint64_t bar;
     const int64_t units = (int64_t)p.n_layers * 2 * p.B * p.H;
@@ -326,6 +334,10 @@ __global__ void __launch_bounds__(128) kv_append_bulk_kernel(const KvParams p) {
     if (active && store_bytes) bulk_s2g(dst, mine, store_bytes);
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // Fused result exchange (multi-GPU): CTA (0,0) -- which pushed this rank's records at its start when
+    // exchange_packed is set -- gathers every rank's records of the epoch once its own rows are copied:
+    // the NVLink round trips overlap the rest of the append instead of trailing it.
+    if (p.xchg && blockIdx.x == 0 && blockIdx.y == 0) exchange_gather_cta(p.xchg, p.xchg_out);
     retire_and_commit(p);
 }
 
@@ -358,7 +370,8 @@ static int kv_append_impl(const sd_kv_layer* layers, const sd_kv_layer* single, 
                           int64_t new_stride_r, const int32_t* seq_lens, int32_t* seq_lens_out,
                           const int32_t* n_keep, int keep_bias, const uint8_t* accepted_mask, int zero_rejected,
                           int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, int early_rows, void* stream,
-                          const sd_exchange* exchange = nullptr, int32_t* exchange_out = nullptr) {
+                          const sd_exchange* exchange = nullptr, int32_t* exchange_out = nullptr,
+                          const int32_t* exchange_packed = nullptr) {
     using namespace sd;
     if (n_layers < 0 || B < 0 || H < 0 || R < 0 || row_bytes <= 0 || capacity < 0) return SD_ERR_INVALID_ARG;
     if (n_layers == 0 || B == 0 || H == 0) return SD_OK;
@@ -394,6 +407,7 @@ static int kv_append_impl(const sd_kv_layer* layers, const sd_kv_layer* single, 
     p.ticket = ticket;
     p.xchg = exchange;
     p.xchg_out = exchange_out;
+    p.xchg_packed = exchange_packed;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
     if (R == 0) {  // nothing offered: only the length commit (identity) is required
@@ -460,13 +474,13 @@ int sd_kv_append(const sd_kv_layer* layers, int n_layers, int B, int H, int R, i
                  int64_t new_stride_h, int64_t new_stride_r, const int32_t* seq_lens, int32_t* seq_lens_out,
                  const int32_t* n_keep, int keep_bias, const uint8_t* accepted_mask, int zero_rejected,
                  int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, int rows_ready_early, void* stream,
-                 const sd_exchange* exchange, int32_t* exchange_out) {
+                 const sd_exchange* exchange, int32_t* exchange_out, const int32_t* exchange_packed) {
     if (n_layers > 0 && !layers) return SD_ERR_INVALID_ARG;
     if (exchange && (n_layers == 0 || B == 0 || H == 0 || R == 0)) return SD_ERR_UNSUPPORTED;  // nothing would launch
     return kv_append_impl(layers, nullptr, 0, n_layers, B, H, R, row_bytes, capacity, arena_stride_b, arena_stride_h,
                           new_stride_b, new_stride_h, new_stride_r, seq_lens, seq_lens_out, n_keep, keep_bias,
                           accepted_mask, zero_rejected, max_seq_len_host, overflow_flag, ticket, rows_ready_early, stream,
-                          exchange, exchange_out);
+                          exchange, exchange_out, exchange_packed);
 }
 
 int sd_kv_append_layer(void* arena_k, void* arena_v, const void* new_k, const void* new_v, int B, int H, int R,

@@ -494,7 +494,7 @@ SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int n
             char* own = reinterpret_cast<char*>(x->peer[x->rank]);
             const unsigned epoch = ld_volatile_u32(reinterpret_cast<const unsigned*>(own));
             const unsigned long long tag = (unsigned long long)(epoch + 1u) << 32;
-            const size_t rec_row = (size_t)(epoch & 1u) * world * x->rows_per_rank + (size_t)x->rank * x->rows_per_rank + b;
+            const size_t rec_row = (size_t)(epoch & 3u) * world * x->rows_per_rank + (size_t)x->rank * x->rows_per_rank + b;
             for (int i = lane; i < world * width; i += 32) {
                 const int pr = i / width, col = i - pr * width;
                 int val = -1;
@@ -502,7 +502,7 @@ SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int n
                 else if (col - 1 < p.rows) val = s_tgt[col - 1];
                 unsigned long long* recs =
                     reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(x->peer[pr]) + kExchangeHeaderBytes);
-                st_volatile_u64(recs + rec_row * width + col, tag | (unsigned)val);
+                recs[rec_row * width + col] = tag | (unsigned)val;  // weak store: posted, pipelined over NVLink
             }
         }
     }

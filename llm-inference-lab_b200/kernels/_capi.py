@@ -48,7 +48,7 @@ SIGNATURES = {
     "sd_verify_set_variant": (_i, [_i, _i]),
     "sd_verify_set_trace": (_i, [_vp, _sz]),
     "sd_kv_append": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp,
-                          _i, _vp, _i, _i64, _vp, _vp, _i, _vp, _vp, _vp]),
+                          _i, _vp, _i, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "sd_kv_append_layer": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                                 _vp, _i, _vp, _i, _vp, _vp]),
     "sd_kv_set_variant": (_i, [_i]),
@@ -74,7 +74,7 @@ class ExchangeDesc(C.Structure):
     """struct sd_exchange (include/sd_verify.h)."""
 
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("rows_per_rank", C.c_int32), ("width", C.c_int32),
-                ("total_rows", C.c_int32), ("reserved", C.c_int32 * 3), ("peer", C.c_void_p * MAX_PEERS)]
+                ("total_rows", C.c_int32), ("lag", C.c_int32), ("reserved", C.c_int32 * 2), ("peer", C.c_void_p * MAX_PEERS)]
 
 
 class SdError(RuntimeError):

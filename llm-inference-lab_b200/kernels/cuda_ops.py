@@ -453,6 +453,7 @@ def kv_arena_append_launch(
     rows_ready_early: bool = False,
     exchange: Optional[int] = None,
     exchange_out: Optional[torch.Tensor] = None,
+    exchange_packed: Optional[torch.Tensor] = None,
 ) -> None:
     """All-layer arena append (sd_kv_append).  ``layer_table`` is a device int64 [n_layers, 4] tensor
     of (arena_k, arena_v, new_k, new_v) pointers == sd_kv_layer[n_layers]."""
@@ -463,7 +464,7 @@ def kv_arena_append_launch(
             layer_table.data_ptr(), n_layers, B, H, R, row_bytes, capacity, arena_strides[0], arena_strides[1],
             new_strides[0], new_strides[1], new_strides[2], _ptr(seq_lens), _ptr(seq_lens_out), _ptr(n_keep),
             keep_bias, _ptr(accepted_mask), int(zero_rejected), max_seq_len_host, _ptr(overflow_flag),
-            ticket.data_ptr(), int(rows_ready_early), _stream_ptr(dev), exchange, _ptr(exchange_out),
+            ticket.data_ptr(), int(rows_ready_early), _stream_ptr(dev), exchange, _ptr(exchange_out), _ptr(exchange_packed),
         )
     lib.check(rc, "sd_kv_append")
 

@@ -106,13 +106,21 @@ class PeerExchange:
     device-side epoch.  No NCCL launch on the step (a NCCL all-gather costs ~15 us on a ~32 us step).
     Pass ``desc_ptr`` to ``cuda_ops.verify_launch(exchange=...)`` / ``VerifyStep(exchange=...)``.
 
-    One ``wait()`` per verify launch, on every rank, in the same order (SPMD); both are graph-capturable."""
+    One ``wait()`` per verify launch, on every rank, in the same order (SPMD); both are graph-capturable.
 
-    def __init__(self, shard: BatchShard, k_draft: int, device, group=None, _peers=None, _own=None) -> None:
+    ``lag=0``: a step gathers its own records, which couples the ranks step by step (each step costs the
+    slowest rank's verify plus the NVLink latency).  ``lag=1``: a step gathers the PREVIOUS step's records:
+    every rank still has its own shard's results immediately (``VerifyStep.packed``), the global table
+    arrives one step later, and the ranks stop running in lockstep (a rank may be one step ahead)."""
+
+    def __init__(self, shard: BatchShard, k_draft: int, device, group=None, lag: int = 0, _peers=None, _own=None) -> None:
         import ctypes as C
 
         from kernels import _capi
 
+        if lag not in (0, 1):
+            raise ValueError("lag must be 0 (gather the step's own records) or 1 (the previous step's)")
+        self.lag = lag
         self.shard, self.K, self.width = shard, k_draft, k_draft + 2
         self.device = torch.device(device)
         self.rows = max(1, shard.max_local_batch)
@@ -145,6 +153,7 @@ class PeerExchange:
             desc = _capi.ExchangeDesc()
             desc.world, desc.rank, desc.rows_per_rank, desc.width = world, rank, self.rows, self.width
             desc.total_rows = shard.global_batch
+            desc.lag = lag
             for r in range(world):
                 desc.peer[r] = peers[r]
             raw = torch.frombuffer(bytearray(bytes(desc)), dtype=torch.uint8)
@@ -157,7 +166,7 @@ class PeerExchange:
         return self.desc.data_ptr()
 
     @classmethod
-    def emulate(cls, world: int, global_batch: int, k_draft: int, device):
+    def emulate(cls, world: int, global_batch: int, k_draft: int, device, lag: int = 0):
         """All ranks inside ONE process on one GPU (tests): the buffers are plain allocations, the peer
         tables point at each other.  Launch every rank's verify BEFORE any rank's wait()."""
         import ctypes as C
@@ -173,7 +182,7 @@ class PeerExchange:
                 ptr = C.c_void_p()
                 lib.check(lib.sd_exchange_alloc(nbytes, C.byref(ptr), None), "sd_exchange_alloc")
                 ptrs.append(ptr.value)
-        out = [cls(s, k_draft, device, _peers=ptrs) for s in shards]
+        out = [cls(s, k_draft, device, lag=lag, _peers=ptrs) for s in shards]
         out[0]._emulated_owned = ptrs  # freed with rank 0's object
         return out
 

@@ -46,7 +46,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert lib.sd_verify_set_tuning(0, 0) == 0
     assert lib.sd_kv_set_variant(7) == -1
     # capacity check on host-known sizes
-    rc = lib.sd_kv_append(1, 1, 1, 1, 5, 256, 8, 0, 0, 0, 0, 0, None, None, None, 0, None, 1, 4, None, 1, 0, None, None, None)
+    rc = lib.sd_kv_append(1, 1, 1, 1, 5, 256, 8, 0, 0, 0, 0, 0, None, None, None, 0, None, 1, 4, None, 1, 0, None, None, None, None)
     assert rc == -6
 
 

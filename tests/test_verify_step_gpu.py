@@ -198,3 +198,80 @@ def test_sampled_bonus_in_the_step(use_graph):
             assert np.isfinite(filt[t])
             lo = cdf[t - 1] if t > 0 else 0.0
             assert lo - 2e-5 <= u[b] < cdf[t] + 2e-5
+
+
+def test_peer_exchange_with_one_step_lag():
+    """lag = 1: the table gathered during step t is step t-1's (nothing at t = 0); 4 slots keep epochs apart."""
+    from scheduler.batch_shard import PeerExchange
+
+    world, global_batch, K, V = 2, 6, 4, 3001
+    xs = PeerExchange.emulate(world, global_batch, K, "cuda", lag=1)
+    try:
+        steps = [VerifyStep(x.shard.local_batch, K, V, exchange=x) for x in xs]
+        for st in steps:
+            st.exchange_wait = False
+        for x in xs:
+            x.out.fill_(-7)
+        prev = None
+        for it in range(7):
+            logits, ids = make_verify_inputs(global_batch, K + 1, K, V, "bf16", p_match=0.6, seed=500 + it, device="cuda")
+            e_acc, _, e_tgt, _ = c_oracle.verify(to_np(logits), "bf16", to_np(ids))
+            want = O.pack_step_result(e_acc, e_tgt)
+            for x, st in zip(xs, steps):
+                s, e = x.shard.bounds()
+                st.logits.copy_(logits[s:e])
+                st.draft_ids.copy_(ids[s:e])
+                st.run()
+            gathered = [x.wait().clone() for x in xs]
+            torch.cuda.synchronize()
+            for r, got in enumerate(gathered):
+                if prev is None:
+                    assert (got.cpu().numpy() == -7).all()  # nothing gathered at the first step
+                else:
+                    np.testing.assert_array_equal(got.cpu().numpy(), prev, err_msg=f"rank {r} step {it}")
+            prev = want
+    finally:
+        for x in xs:
+            x.close()
+
+
+def test_peer_exchange_pushed_and_gathered_by_the_append_launch():
+    """exchange_packed: the FIRST CTA of kv_append pushes this rank's records, its LAST CTA gathers.  Ranks
+    emulated in one process can only run this with lag = 1 (with lag 0 a rank's append would spin on a
+    push that is launched after it); real ranks are checked by tools/check_peer_exchange.py."""
+    from scheduler.batch_shard import PeerExchange
+
+    world, K, V, layers, H, D, L, cap = 2, 4, 2053, 2, 2, 64, 5, 64
+    global_batch = 6
+    xs = PeerExchange.emulate(world, global_batch, K, "cuda", lag=1)
+    try:
+        arenas, steps = [], []
+        for x in xs:
+            n = x.shard.local_batch
+            a = KVArena(layers, n, H, D, cap, K + 1, torch.bfloat16, "cuda")
+            a.set_lengths([L] * n)
+            arenas.append(a)
+            steps.append(VerifyStep(n, K, V, arena=None))  # the verify launch does not carry the exchange
+            x.out.fill_(-7)
+        prev = None
+        for it in range(5):
+            logits, ids = make_verify_inputs(global_batch, K + 1, K, V, "bf16", p_match=0.7, seed=700 + it, device="cuda")
+            e_acc, _, e_tgt, _ = c_oracle.verify(to_np(logits), "bf16", to_np(ids))
+            want = O.pack_step_result(e_acc, e_tgt)
+            for x, st, a in zip(xs, steps, arenas):
+                s, e = x.shard.bounds()
+                st.logits.copy_(logits[s:e])
+                st.draft_ids.copy_(ids[s:e])
+                st.run()
+                a.append(st.accept_len, keep_bias=1, exchange=x, exchange_packed=st.packed)
+            torch.cuda.synchronize()
+            for r, x in enumerate(xs):
+                got = x.unpad(x.out).cpu().numpy()
+                if prev is None:
+                    assert (got == -7).all()
+                else:
+                    np.testing.assert_array_equal(got, prev, err_msg=f"rank {r} step {it}")
+            prev = want
+    finally:
+        for x in xs:
+            x.close()

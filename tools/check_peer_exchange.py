@@ -112,6 +112,12 @@ def main():
         arena.seq_lens.copy_(lens0)
         arena.append(st.accept_len, keep_bias=1, check_capacity=False, exchange=peer)
 
+    def step_fused_kv_push():  # verify (no exchange) -> kv_append: first CTA pushes, last CTA gathers
+        st.exchange = None
+        st.run()
+        arena.seq_lens.copy_(lens0)
+        arena.append(st.accept_len, keep_bias=1, check_capacity=False, exchange=peer, exchange_packed=st.packed)
+
     def step_plain():
         st.exchange = None
         st.run()
@@ -124,6 +130,14 @@ def main():
 
     t_peer, t_nccl, t_none = timed(step_peer), timed(step_nccl), timed(step_none)
     t_fused, t_plain, t_plain_nccl = timed(step_fused), timed(step_plain), timed(step_plain_nccl)
+    t_fused_kv = timed(step_fused_kv_push)
+    step_fused_kv_push()
+    got = peer.out.clone()
+    want = nccl.all_gather(st.packed).clone()
+    torch.cuda.synchronize()
+    if not torch.equal(got, want):
+        bad += 1
+        print(f"[rank {rank}] kv-side push: MISMATCH", flush=True)
     # correctness of the fused path once more after the timing loops
     st.exchange = peer
     st.run()
@@ -141,7 +155,7 @@ def main():
         print(json.dumps({"world": world, "mismatches": int(ok.item()), "verify_only_us": t_none,
                           "verify_plus_peer_exchange_us": t_peer, "verify_plus_nccl_allgather_us": t_nccl,
                           "step_verify_kv_us": t_plain, "step_with_fused_exchange_us": t_fused,
-                          "step_with_nccl_allgather_us": t_plain_nccl}), flush=True)
+                          "step_with_nccl_allgather_us": t_plain_nccl, "step_with_kv_side_push_us": t_fused_kv}), flush=True)
     torch.cuda.synchronize()
     sys.stdout.flush()
     os._exit(0 if int(ok.item()) == 0 else 1)
