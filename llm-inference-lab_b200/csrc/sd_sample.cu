@@ -77,8 +77,8 @@ SD_DEVINL ScanPair block_exclusive_scan(ScanPair v, ScanPair& total, unsigned lo
     }
     __syncthreads();
     if (wid == 0) {
-        unsigned long long wm = s_mass[lane];
-        unsigned wc = s_cnt[lane];
+        unsigned long long wm = lane < kSampWarps ? s_mass[lane] : 0ull;
+        unsigned wc = lane < kSampWarps ? s_cnt[lane] : 0u;
         unsigned long long im = wm;
         unsigned ic = wc;
 #pragma unroll
@@ -107,12 +107,327 @@ SD_DEVINL ScanPair block_exclusive_scan(ScanPair v, ScanPair& total, unsigned lo
     return ex;
 }
 
+// ---- row accessors: the same selection / draw code runs over the logits row in global memory and over
+// the compacted top-k candidates in shared memory ----
+template <typename T>
+struct GlobalRow {
+    const T* row;
+    int n;
+    SD_DEVINL int size() const { return n; }
+    SD_DEVINL int token(int i) const { return i; }
+    // 8 consecutive elements starting at i0 (a multiple of 8); one 16-byte load when the address allows it
+    SD_DEVINL void load8(int i0, float (&xs)[8], bool (&ok)[8]) const {
+        if constexpr (sizeof(T) == 2) {
+            if (i0 + 8 <= n && (reinterpret_cast<uintptr_t>(row + i0) & 15u) == 0) {
+                const uint4 v = *reinterpret_cast<const uint4*>(row + i0);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                        xs[2 * q] = __uint_as_float(w[q] << 16);
+                        xs[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+                    } else {
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+                        xs[2 * q] = f.x;
+                        xs[2 * q + 1] = f.y;
+                    }
+                    ok[2 * q] = ok[2 * q + 1] = true;
+                }
+                return;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            ok[e] = i0 + e < n;
+            xs[e] = ok[e] ? to_float<T>(row[i0 + e]) : 0.f;
+        }
+    }
+};
+
+struct CompactRow {
+    const float* x;
+    const int* idx;
+    int n;
+    SD_DEVINL int size() const { return n; }
+    SD_DEVINL int token(int i) const { return idx[i]; }
+    SD_DEVINL void load8(int i0, float (&xs)[8], bool (&ok)[8]) const {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            ok[e] = i0 + e < n;
+            xs[e] = ok[e] ? x[i0 + e] : 0.f;
+        }
+    }
+};
+
+// shared scratch of one CTA
+struct SampShared {
+    unsigned* h_cnt;             // [warps][256]
+    unsigned long long* h_mass;  // [warps][256]
+    unsigned long long* s_mass;  // [33]
+    unsigned* s_cnt;             // [33]
+    unsigned* tot_cnt;           // [256]
+    unsigned long long* tot_mass;  // [256]
+    uint32_t* s_u32;             // [4]
+    unsigned long long* s_u64;   // [2]
+};
+
+constexpr int kBatch = 2;                 // tiles whose loads are issued together (memory-level parallelism)
+constexpr int kTile = kSampThreads * 8;  // elements per tile: thread t owns [t*8, t*8+8) of the tile (index order)
+
+// Radix select over the order keys of the elements inside `outer` (a previously selected prefix):
+//   by_mass == false: largest prefix of the descending order with at most `k_target` elements
+//   by_mass == true : largest prefix whose mass is <= mass_target (at least one element)
+template <typename Row>
+SD_DEVINL SelectResult radix_select(const Row& R, const SampShared& sh, const SampleParams& p, float m, bool by_mass,
+                                    unsigned k_target, unsigned long long mass_target, const SelectResult outer,
+                                    bool has_outer) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = R.size();
+    uint32_t prefix = 0u, prefix_mask = 0u;
+    unsigned cnt_above = 0;  // elements with key above the current prefix range (all kept)
+    unsigned long long mass_above = 0ull;
+    for (int d = 0; d < p.ndigits; ++d) {
+        const int shift = 24 - 8 * d;
+        for (int i = tid; i < kSampWarps * kBins; i += kSampThreads) {
+            sh.h_cnt[i] = 0u;
+            sh.h_mass[i] = 0ull;
+        }
+        __syncthreads();
+        // Elements equal to outer.tau are all counted here although the outer prefix keeps only n_ties of
+        // them; the bucket that holds outer.tau is clamped in the last digit pass (in earlier passes the
+        // over-count can only make the walk descend into the lowest bucket, which the last pass corrects).
+        for (int t0 = 0; t0 < n; t0 += kTile * kBatch) {
+            float xs[kBatch][8];
+            bool ok[kBatch][8];
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q) R.load8(t0 + q * kTile + tid * 8, xs[q], ok[q]);  // kBatch tiles in flight
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    unsigned bin = 0xffffffffu;
+                    const uint32_t k = order_key(xs[q][e]);
+                    if (ok[q][e] && !(has_outer && k < outer.tau) && (k & prefix_mask) == prefix) bin = (k >> shift) & 0xffu;
+                    if (by_mass) {
+                        if (bin != 0xffffffffu) {
+                            atomicAdd(&sh.h_cnt[wid * kBins + bin], 1u);
+                            atomicAdd(&sh.h_mass[wid * kBins + bin], fixed_mass(xs[q][e], m, p.inv_t_log2));
+                        }
+                    } else {
+                        // warp-aggregated count: logits share their exponent byte, so most lanes hit one bin
+                        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+                        if (bin != 0xffffffffu && lane == __ffs(peers) - 1)
+                            atomicAdd(&sh.h_cnt[wid * kBins + bin], __popc(peers));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < kBins) {
+            unsigned c = 0;
+            unsigned long long w = 0ull;
+            for (int q = 0; q < kSampWarps; ++q) {
+                c += sh.h_cnt[q * kBins + tid];
+                w += sh.h_mass[q * kBins + tid];
+            }
+            sh.tot_cnt[tid] = c;
+            sh.tot_mass[tid] = w;
+        }
+        __syncthreads();
+        if (has_outer && tid == 0 && (outer.tau & prefix_mask) == prefix && d == p.ndigits - 1) {
+            const unsigned bin = (outer.tau >> shift) & 0xffu;
+            if (sh.tot_cnt[bin] > outer.n_ties) {
+                const unsigned long long each = sh.tot_cnt[bin] ? sh.tot_mass[bin] / sh.tot_cnt[bin] : 0ull;
+                sh.tot_cnt[bin] = outer.n_ties;
+                sh.tot_mass[bin] = each * outer.n_ties;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {  // walk the 256 buckets from the top
+            unsigned c = cnt_above;
+            unsigned long long w = mass_above;
+            int chosen = -1;  // -1: nothing crosses, the whole candidate range is kept
+            for (int bin = kBins - 1; bin >= 0; --bin) {
+                const unsigned c2 = c + sh.tot_cnt[bin];
+                const unsigned long long w2 = w + sh.tot_mass[bin];
+                const bool over = by_mass ? (w2 > mass_target) : (c2 > k_target);
+                if (sh.tot_cnt[bin] && over) {
+                    chosen = bin;
+                    break;
+                }
+                c = c2;
+                w = w2;
+            }
+            sh.s_u32[0] = (uint32_t)chosen;
+            sh.s_u32[1] = c;
+            sh.s_u64[0] = w;
+        }
+        __syncthreads();
+        const int chosen = (int)sh.s_u32[0];
+        cnt_above = sh.s_u32[1];
+        mass_above = sh.s_u64[0];
+        __syncthreads();
+        if (chosen < 0) {
+            SelectResult all;
+            all.tau = has_outer ? outer.tau : 0u;
+            all.n_ties = has_outer ? outer.n_ties : 0xffffffffu;
+            return all;
+        }
+        prefix |= (uint32_t)chosen << shift;
+        prefix_mask |= 0xffu << shift;
+    }
+    // The digits examined cover every information bit of the input type, so the chosen bucket of the last
+    // pass IS one value: its count is the number of ties, and the key bits below the examined digits follow
+    // from the sign (order_key: positive -> bits of x, zero-extended; negative -> complement, one-extended).
+    SelectResult res;
+    const uint32_t low_mask = ~prefix_mask;
+    res.tau = (prefix & 0x80000000u) ? prefix : (prefix | low_mask);
+    if (tid == 0) {
+        unsigned t = sh.tot_cnt[(prefix >> (24 - 8 * (p.ndigits - 1))) & 0xffu];  // already clamped to the outer prefix
+        if (has_outer && res.tau == outer.tau && t > outer.n_ties) t = outer.n_ties;
+        unsigned keep;
+        if (by_mass) {
+            const unsigned long long each = fixed_mass(key_to_float(res.tau), m, p.inv_t_log2);
+            const unsigned long long room = mass_target > mass_above ? mass_target - mass_above : 0ull;
+            const unsigned long long fit = each ? room / each : (unsigned long long)t;
+            keep = fit > t ? t : (unsigned)fit;
+            if (cnt_above == 0 && keep == 0) keep = 1;  // "keep at least one token" (pipeline.py:115)
+        } else {
+            keep = k_target > cnt_above ? k_target - cnt_above : 0u;
+            if (keep > t) keep = t;
+        }
+        sh.s_u32[3] = keep == t ? 0xffffffffu : keep;  // every tie kept: no index ranking needed downstream
+    }
+    __syncthreads();
+    res.n_ties = sh.s_u32[3];
+    __syncthreads();
+    return res;
+}
+
+// One index-ordered pass over the row: visits every element with its membership in the (tau, n_ties)
+// prefix `s` (tie ranks by index via a block scan per tile).  `visit(tile_base, xs, ok, keep)` is called by
+// every thread once per tile and may itself contain block-wide collectives.
+template <typename Row, typename Visit>
+SD_DEVINL void for_each_kept(const Row& R, const SampShared& sh, const SelectResult& s, bool restricted, Visit&& visit) {
+    const int tid = threadIdx.x;
+    const bool rank_ties = restricted && s.n_ties != 0xffffffffu;  // else: keep = key >= tau, no scan needed
+    unsigned run_ties = 0;
+    for (int tb = 0; tb < R.size(); tb += kTile * kBatch) {
+        float xs[kBatch][8];
+        bool ok[kBatch][8];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) R.load8(tb + q * kTile + tid * 8, xs[q], ok[q]);  // kBatch tiles in flight
+        bool go_on = true;
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+            const int t0 = tb + q * kTile;
+            if (t0 >= R.size() || !go_on) continue;  // uniform across the CTA
+            bool keep[8];
+            uint32_t ks[8];
+            unsigned my_ties = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                ks[e] = order_key(xs[q][e]);
+                if (ok[q][e] && rank_ties && ks[e] == s.tau) ++my_ties;
+            }
+            unsigned rank = 0;
+            if (rank_ties) {
+                ScanPair v{0ull, my_ties}, total;
+                const ScanPair ex = block_exclusive_scan(v, total, sh.s_mass, sh.s_cnt);
+                rank = run_ties + ex.cnt;
+                run_ties += total.cnt;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                keep[e] = ok[q][e];
+                if (ok[q][e] && restricted) {
+                    keep[e] = rank_ties ? in_prefix(ks[e], rank, s) : ks[e] >= s.tau;
+                    if (rank_ties && ks[e] == s.tau) ++rank;
+                }
+            }
+            go_on = visit(t0, xs[q], keep);
+        }
+        if (!go_on) break;
+    }
+}
+
+template <typename Row>
+SD_DEVINL unsigned long long kept_mass_total(const Row& R, const SampShared& sh, const SampleParams& p, float m,
+                                             const SelectResult& s, bool restricted) {
+    unsigned long long mine = 0ull;
+    for_each_kept(R, sh, s, restricted, [&](int, const float (&xs)[8], const bool (&keep)[8]) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (keep[e]) mine += fixed_mass(xs[e], m, p.inv_t_log2);
+        return true;
+    });
+    ScanPair v{mine, 0u}, total;
+    block_exclusive_scan(v, total, sh.s_mass, sh.s_cnt);
+    return total.mass;
+}
+
+// top-p (optional) + inverse-CDF draw over the kept prefix `sel` of row R.  Returns the TOKEN id on thread 0
+// (0xffffffff if the fixed-point rounding left the target past the end) and the kept-set size.
+template <typename Row>
+SD_DEVINL void nucleus_and_draw(const Row& R, const SampShared& sh, const SampleParams& p, float m, SelectResult sel,
+                                bool has_sel, float u, bool want_count, uint32_t& token_out, unsigned& kept_out) {
+    const int tid = threadIdx.x;
+    if (p.top_p < 1.0f) {
+        const unsigned long long z1 = kept_mass_total(R, sh, p, m, sel, has_sel);
+        // cumulative probability <= top_p  <=>  cumulative mass <= top_p * Z1
+        const unsigned long long target = (unsigned long long)((double)p.top_p * (double)z1);
+        SelectResult nucleus = radix_select(R, sh, p, m, true, 0u, target, sel, has_sel);
+        if (has_sel && nucleus.tau == sel.tau && nucleus.n_ties > sel.n_ties) nucleus.n_ties = sel.n_ties;
+        sel = nucleus;
+        has_sel = true;
+    }
+    const unsigned long long z = kept_mass_total(R, sh, p, m, sel, has_sel);
+    u = u < 0.f ? 0.f : (u > 0.99999994f ? 0.99999994f : u);
+    const unsigned long long target = (unsigned long long)((double)u * (double)z);
+    if (tid == 0) sh.s_u32[0] = 0xffffffffu;
+    __syncthreads();
+    unsigned long long run_mass = 0ull;
+    unsigned run_kept = 0;
+    for_each_kept(R, sh, sel, has_sel, [&](int t0, const float (&xs)[8], const bool (&keep)[8]) {
+        unsigned long long w[8];
+        unsigned long long mine = 0ull;
+        unsigned mine_kept = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            w[e] = keep[e] ? fixed_mass(xs[e], m, p.inv_t_log2) : 0ull;
+            mine += w[e];
+            mine_kept += keep[e] ? 1u : 0u;
+        }
+        ScanPair v{mine, mine_kept}, total;
+        const ScanPair ex = block_exclusive_scan(v, total, sh.s_mass, sh.s_cnt);
+        const unsigned long long before = run_mass + ex.mass;
+        if (before <= target && target < before + mine) {  // exactly one thread owns the target
+            unsigned long long c = before;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (w[e] && target < c + w[e]) {
+                    sh.s_u32[0] = (uint32_t)R.token(t0 + tid * 8 + e);
+                    break;
+                }
+                c += w[e];
+            }
+        }
+        run_mass += total.mass;
+        run_kept += total.cnt;
+        __syncthreads();
+        return want_count || sh.s_u32[0] == 0xffffffffu;  // early exit once drawn, unless the set size is wanted
+    });
+    __syncthreads();
+    token_out = sh.s_u32[0];
+    kept_out = run_kept;
+    __syncthreads();
+}
+
+constexpr int kCompactCap = 1024;  // top-k values up to this size continue on a compacted candidate list in smem
+
 template <typename T>
 __global__ void __launch_bounds__(kSampThreads) sample_bonus_kernel(const SampleParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // per-warp private histograms: counts [warps][256] u32, masses [warps][256] u64
-    unsigned* h_cnt = reinterpret_cast<unsigned*>(smem_raw);
-    unsigned long long* h_mass = reinterpret_cast<unsigned long long*>(smem_raw + kSampWarps * kBins * 4);
     __shared__ unsigned long long s_mass[33];
     __shared__ unsigned s_cnt[33];
     __shared__ unsigned tot_cnt[kBins];
@@ -121,6 +436,17 @@ __global__ void __launch_bounds__(kSampThreads) sample_bonus_kernel(const Sample
     __shared__ unsigned long long s_u64[2];
     __shared__ uint32_t s_rkey[kSampWarps];
     __shared__ int s_rpos[kSampWarps];
+    SampShared sh;
+    sh.h_cnt = reinterpret_cast<unsigned*>(smem_raw);
+    sh.h_mass = reinterpret_cast<unsigned long long*>(smem_raw + kSampWarps * kBins * 4);
+    float* cand_x = reinterpret_cast<float*>(smem_raw + kSampWarps * kBins * 12);
+    int* cand_idx = reinterpret_cast<int*>(cand_x + kCompactCap);
+    sh.s_mass = s_mass;
+    sh.s_cnt = s_cnt;
+    sh.tot_cnt = tot_cnt;
+    sh.tot_mass = tot_mass;
+    sh.s_u32 = s_u32;
+    sh.s_u64 = s_u64;
 
     pdl_wait();
     pdl_trigger();
@@ -131,32 +457,44 @@ __global__ void __launch_bounds__(kSampThreads) sample_bonus_kernel(const Sample
         r = p.row_index[b] + p.row_bias;
         r = r < 0 ? 0 : (r >= p.rows ? p.rows - 1 : r);
     }
-    const T* row = reinterpret_cast<const T*>(p.logits) + (int64_t)b * p.stride_b + (int64_t)r * p.stride_r;
+    GlobalRow<T> G;
+    G.row = reinterpret_cast<const T*>(p.logits) + (int64_t)b * p.stride_b + (int64_t)r * p.stride_r;
+    G.n = p.V;
     const int V = p.V;
 
     // ---- pass A: maximum (order key) and its first index ----
     uint32_t kmax = 0u;
     int amax = 0x7fffffff;
-    for (int i = tid; i < V; i += kSampThreads) {
-        const uint32_t k = order_key(to_float<T>(row[i]));
-        if (k > kmax) {  // strictly greater: the first index wins within a thread (indices ascend)
-            kmax = k;
-            amax = i;
+    for (int tb = 0; tb < V; tb += kTile * kBatch) {
+        float xs[kBatch][8];
+        bool ok[kBatch][8];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) G.load8(tb + q * kTile + tid * 8, xs[q], ok[q]);
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const uint32_t k = order_key(xs[q][e]);
+                if (ok[q][e] && k > kmax) {  // strictly greater: indices ascend within a thread, the first one wins
+                    kmax = k;
+                    amax = tb + q * kTile + tid * 8 + e;
+                }
+            }
         }
     }
     {
-        uint32_t wk = __reduce_max_sync(0xffffffffu, kmax);
-        unsigned wp = __reduce_min_sync(0xffffffffu, kmax == wk ? (unsigned)amax : 0x7fffffffu);
+        const uint32_t wk = __reduce_max_sync(0xffffffffu, kmax);
+        const unsigned wp = __reduce_min_sync(0xffffffffu, kmax == wk ? (unsigned)amax : 0x7fffffffu);
         if (lane == 0) {
             s_rkey[wid] = wk;
             s_rpos[wid] = (int)wp;
         }
         __syncthreads();
         if (wid == 0) {
-            uint32_t k2 = s_rkey[lane];
-            unsigned p2 = (unsigned)s_rpos[lane];
-            uint32_t bk = __reduce_max_sync(0xffffffffu, k2);
-            unsigned bp = __reduce_min_sync(0xffffffffu, k2 == bk ? p2 : 0x7fffffffu);
+            const uint32_t k2 = lane < kSampWarps ? s_rkey[lane] : 0u;
+            const unsigned p2 = lane < kSampWarps ? (unsigned)s_rpos[lane] : 0x7fffffffu;
+            const uint32_t bk = __reduce_max_sync(0xffffffffu, k2);
+            const unsigned bp = __reduce_min_sync(0xffffffffu, k2 == bk ? p2 : 0x7fffffffu);
             if (lane == 0) {
                 s_u32[0] = bk;
                 s_u32[1] = bp;
@@ -175,273 +513,59 @@ __global__ void __launch_bounds__(kSampThreads) sample_bonus_kernel(const Sample
         return;
     }
     const float m = key_to_float(kmax);
-
-    // Radix select over the order keys of the elements inside `outer` (a previously selected prefix):
-    //   by_mass == false: largest prefix of the descending order with at most `k_target` elements
-    //   by_mass == true : largest prefix whose mass is <= mass_target (at least one element)
-    auto radix_select = [&](bool by_mass, unsigned k_target, unsigned long long mass_target,
-                            const SelectResult& outer, bool has_outer) -> SelectResult {
-        uint32_t prefix = 0u, prefix_mask = 0u;
-        unsigned cnt_above = 0;               // elements with key > current prefix range (all kept)
-        unsigned long long mass_above = 0ull;
-        for (int d = 0; d < p.ndigits; ++d) {
-            const int shift = 24 - 8 * d;
-            for (int i = tid; i < kSampWarps * kBins; i += kSampThreads) {
-                h_cnt[i] = 0u;
-                h_mass[i] = 0ull;
-            }
-            __syncthreads();
-            // NOTE: ties of `outer` are ordered by index; an element equal to outer.tau is inside the outer
-            // prefix only if its tie rank is < outer.n_ties.  Tie ranks need an index-ordered count, which
-            // the histogram passes do not have; instead the outer threshold bucket is handled exactly
-            // below: elements with key == outer.tau enter the histogram with weight (n_ties / n_equal),
-            // realised by counting them all here and clamping the bucket totals afterwards.
-            for (int i = tid; i < V; i += kSampThreads) {
-                const float x = to_float<T>(row[i]);
-                const uint32_t k = order_key(x);
-                if (has_outer && k < outer.tau) continue;
-                if ((k & prefix_mask) != prefix) continue;
-                const unsigned bin = (k >> shift) & 0xffu;
-                atomicAdd(&h_cnt[wid * kBins + bin], 1u);
-                if (by_mass) atomicAdd(&h_mass[wid * kBins + bin], fixed_mass(x, m, p.inv_t_log2));
-            }
-            __syncthreads();
-            if (tid < kBins) {
-                unsigned c = 0;
-                unsigned long long w = 0ull;
-                for (int q = 0; q < kSampWarps; ++q) {
-                    c += h_cnt[q * kBins + tid];
-                    w += h_mass[q * kBins + tid];
-                }
-                tot_cnt[tid] = c;
-                tot_mass[tid] = w;
-            }
-            __syncthreads();
-            // the bucket holding outer.tau may contain more ties than the outer prefix keeps: clamp it
-            if (has_outer && tid == 0 && (outer.tau & prefix_mask) == prefix && d == p.ndigits - 1) {
-                const unsigned bin = (outer.tau >> shift) & 0xffu;
-                if (tot_cnt[bin] > outer.n_ties) {
-                    const unsigned long long each = tot_cnt[bin] ? tot_mass[bin] / tot_cnt[bin] : 0ull;
-                    tot_cnt[bin] = outer.n_ties;
-                    tot_mass[bin] = each * outer.n_ties;
-                }
-            }
-            __syncthreads();
-            if (tid == 0) {  // walk the 256 buckets from the top
-                unsigned c = cnt_above;
-                unsigned long long w = mass_above;
-                int chosen = 0;
-                for (int bin = kBins - 1; bin >= 0; --bin) {
-                    const unsigned c2 = c + tot_cnt[bin];
-                    const unsigned long long w2 = w + tot_mass[bin];
-                    const bool over = by_mass ? (w2 > mass_target) : (c2 > k_target);
-                    if (tot_cnt[bin] && over) {
-                        chosen = bin;
-                        break;
-                    }
-                    c = c2;
-                    w = w2;
-                    chosen = bin;  // everything fits: end on the lowest non-crossing bucket
-                    if (bin == 0) {
-                        // nothing crossed: the whole candidate range is kept; signal with bin = -1
-                        chosen = -1;
-                    }
-                }
-                s_u32[0] = (uint32_t)chosen;
-                s_u32[1] = c;
-                s_u64[0] = w;
-            }
-            __syncthreads();
-            const int chosen = (int)s_u32[0];
-            cnt_above = s_u32[1];
-            mass_above = s_u64[0];
-            __syncthreads();
-            if (chosen < 0) {
-                // every candidate is kept: the prefix is the outer prefix itself (or everything)
-                SelectResult all;
-                all.tau = has_outer ? outer.tau : 0u;
-                all.n_ties = has_outer ? outer.n_ties : 0xffffffffu;
-                return all;
-            }
-            prefix |= (uint32_t)chosen << shift;
-            prefix_mask |= 0xffu << shift;
-        }
-        // prefix is now an exact key value (for 16-bit inputs the low 16 bits of every candidate key are a
-        // constant pattern that the selected prefix does not include: recover the full key from one
-        // candidate below).  Elements with key > tau: cnt_above / mass_above.  Ties at tau:
-        SelectResult res;
-        // full key of the threshold: any element matching the prefix (all such elements are equal in
-        // the digits examined; for ndigits == 2 they are equal altogether because the inputs are 16 bit)
-        if (tid == 0) s_u32[2] = 0u;
-        __syncthreads();
-        for (int i = tid; i < V; i += kSampThreads) {
-            const uint32_t k = order_key(to_float<T>(row[i]));
-            if ((k & prefix_mask) == prefix) s_u32[2] = k;  // benign race: all writers store the same value
-        }
-        __syncthreads();
-        res.tau = s_u32[2];
-        __syncthreads();
-        // number of ties available at tau inside the outer prefix, and mass of one tie
-        unsigned n_equal = 0;
-        for (int i = tid; i < V; i += kSampThreads) n_equal += order_key(to_float<T>(row[i])) == res.tau ? 1u : 0u;
-        n_equal = __reduce_add_sync(0xffffffffu, n_equal);
-        if (lane == 0) s_cnt[wid] = n_equal;
-        __syncthreads();
-        if (tid == 0) {
-            unsigned t = 0;
-            for (int q = 0; q < kSampWarps; ++q) t += s_cnt[q];
-            if (has_outer && res.tau == outer.tau && t > outer.n_ties) t = outer.n_ties;
-            unsigned keep;
-            if (by_mass) {
-                const unsigned long long each = fixed_mass(key_to_float(res.tau), m, p.inv_t_log2);
-                const unsigned long long room = mass_target > mass_above ? mass_target - mass_above : 0ull;
-                unsigned long long fit = each ? room / each : (unsigned long long)t;
-                keep = fit > t ? t : (unsigned)fit;
-                if (cnt_above == 0 && keep == 0) keep = 1;  // "keep at least one token" (pipeline.py:115)
-            } else {
-                keep = k_target > cnt_above ? k_target - cnt_above : 0u;
-                if (keep > t) keep = t;
-            }
-            s_u32[3] = keep;
-        }
-        __syncthreads();
-        res.n_ties = s_u32[3];
-        __syncthreads();
-        return res;
-    };
+    const float u = p.uniform[b];
+    const bool want_count = p.kept_count != nullptr;
 
     SelectResult sel;
     sel.tau = 0u;
     sel.n_ties = 0xffffffffu;  // everything
     bool has_sel = false;
+    uint32_t token = 0xffffffffu;
+    unsigned kept = 0;
     if (p.top_k > 0 && p.top_k < V) {
-        sel = radix_select(false, (unsigned)p.top_k, 0ull, sel, false);
+        sel = radix_select(G, sh, p, m, false, (unsigned)p.top_k, 0ull, sel, false);
         has_sel = true;
-    }
-
-    // ---- index-ordered passes over the kept set: total mass, then (optionally) the nucleus, then the draw ----
-    // Tiles of 1024 x 8 consecutive elements keep the index order inside the block scan.
-    auto kept_mass_total = [&](const SelectResult& s, bool restricted) -> unsigned long long {
-        unsigned long long run_mass = 0ull;
-        unsigned run_ties = 0;
-        for (int t0 = 0; t0 < V; t0 += kSampThreads * 8) {
-            const int i0 = t0 + tid * 8;
-            float xs[8];
-            uint32_t ks[8];
-            unsigned my_ties = 0;
+        if (p.top_k <= kCompactCap) {
+            // compact the <= top_k survivors (index order) into shared memory and finish there: top-p and the
+            // draw then touch <= 1024 elements instead of the whole row
+            unsigned run = 0;
+            for_each_kept(G, sh, sel, true, [&](int t0, const float (&xs)[8], const bool (&keep)[8]) {
+                unsigned mine = 0;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int i = i0 + e;
-                xs[e] = i < V ? to_float<T>(row[i]) : 0.f;
-                ks[e] = i < V ? order_key(xs[e]) : 0u;
-                if (i < V && restricted && ks[e] == s.tau) ++my_ties;
-            }
-            ScanPair v{0ull, my_ties}, total;
-            ScanPair ex = block_exclusive_scan(v, total, s_mass, s_cnt);
-            unsigned rank = run_ties + ex.cnt;
-            unsigned long long mine = 0ull;
+                for (int e = 0; e < 8; ++e) mine += keep[e] ? 1u : 0u;
+                ScanPair v{0ull, mine}, total;
+                const ScanPair ex = block_exclusive_scan(v, total, sh.s_mass, sh.s_cnt);
+                unsigned pos = run + ex.cnt;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int i = i0 + e;
-                if (i >= V) continue;
-                bool keep = true;
-                if (restricted) {
-                    keep = in_prefix(ks[e], rank, s);
-                    if (ks[e] == s.tau) ++rank;
+                for (int e = 0; e < 8; ++e) {
+                    if (keep[e] && pos < (unsigned)kCompactCap) {
+                        cand_x[pos] = xs[e];
+                        cand_idx[pos] = t0 + tid * 8 + e;
+                        ++pos;
+                    }
                 }
-                if (keep) mine += fixed_mass(xs[e], m, p.inv_t_log2);
-            }
-            // block sum of `mine`
-            ScanPair v2{mine, 0u}, total2;
-            block_exclusive_scan(v2, total2, s_mass, s_cnt);
-            run_mass += total2.mass;
-            run_ties += total.cnt;
+                run += total.cnt;
+                return true;
+            });
+            __syncthreads();
+            CompactRow C;
+            C.x = cand_x;
+            C.idx = cand_idx;
+            C.n = (int)(run < (unsigned)kCompactCap ? run : (unsigned)kCompactCap);
+            SelectResult all;
+            all.tau = 0u;
+            all.n_ties = 0xffffffffu;
+            nucleus_and_draw(C, sh, p, m, all, false, u, want_count, token, kept);
+        } else {
+            nucleus_and_draw(G, sh, p, m, sel, true, u, want_count, token, kept);
         }
-        return run_mass;
-    };
-
-    if (p.top_p < 1.0f) {
-        const unsigned long long z1 = kept_mass_total(sel, has_sel);
-        // cumulative probability <= top_p  <=>  cumulative mass <= top_p * Z1
-        const unsigned long long target = (unsigned long long)((double)p.top_p * (double)z1);
-        SelectResult nucleus = radix_select(true, 0u, target, sel, has_sel);
-        if (has_sel && nucleus.tau == sel.tau && nucleus.n_ties > sel.n_ties) nucleus.n_ties = sel.n_ties;
-        sel = nucleus;
-        has_sel = true;
-    }
-
-    // ---- the draw: first index whose cumulative kept mass exceeds u * Z ----
-    const unsigned long long z = kept_mass_total(sel, has_sel);
-    float u = p.uniform[b];
-    u = u < 0.f ? 0.f : (u > 0.99999994f ? 0.99999994f : u);
-    const unsigned long long target = (unsigned long long)((double)u * (double)z);
-    if (tid == 0) {
-        s_u32[0] = 0xffffffffu;  // result index
-        s_u32[1] = 0u;           // kept count
-    }
-    __syncthreads();
-    unsigned long long run_mass = 0ull;
-    unsigned run_ties = 0, run_kept = 0;
-    bool done = false;
-    for (int t0 = 0; t0 < V && !done; t0 += kSampThreads * 8) {
-        const int i0 = t0 + tid * 8;
-        float xs[8];
-        uint32_t ks[8];
-        unsigned my_ties = 0;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int i = i0 + e;
-            xs[e] = i < V ? to_float<T>(row[i]) : 0.f;
-            ks[e] = i < V ? order_key(xs[e]) : 0u;
-            if (i < V && has_sel && ks[e] == sel.tau) ++my_ties;
-        }
-        ScanPair v{0ull, my_ties}, total;
-        ScanPair ex = block_exclusive_scan(v, total, s_mass, s_cnt);
-        unsigned rank = run_ties + ex.cnt;
-        unsigned long long w[8];
-        unsigned long long mine = 0ull;
-        unsigned mine_kept = 0;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int i = i0 + e;
-            w[e] = 0ull;
-            if (i >= V) continue;
-            bool keep = true;
-            if (has_sel) {
-                keep = in_prefix(ks[e], rank, sel);
-                if (ks[e] == sel.tau) ++rank;
-            }
-            if (keep) {
-                w[e] = fixed_mass(xs[e], m, p.inv_t_log2);
-                mine += w[e];
-                ++mine_kept;
-            }
-        }
-        ScanPair v2{mine, mine_kept}, total2;
-        ScanPair ex2 = block_exclusive_scan(v2, total2, s_mass, s_cnt);
-        // does the target fall inside this thread's 8 elements?
-        unsigned long long before = run_mass + ex2.mass;
-        if (s_u32[0] == 0xffffffffu && before <= target && target < before + mine) {
-            unsigned long long c = before;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                if (w[e] && target < c + w[e]) {
-                    s_u32[0] = (uint32_t)(i0 + e);  // exactly one thread satisfies the interval test
-                    break;
-                }
-                c += w[e];
-            }
-        }
-        run_mass += total2.mass;
-        run_ties += total.cnt;
-        run_kept += total2.cnt;
-        __syncthreads();
-        if (s_u32[0] != 0xffffffffu && !p.kept_count) done = true;  // early exit unless the set size is wanted
+    } else {
+        nucleus_and_draw(G, sh, p, m, sel, has_sel, u, want_count, token, kept);
     }
     if (tid == 0) {
         // rounding of the fixed-point masses can leave the target at the very end: fall back to the argmax
-        p.out[b] = s_u32[0] == 0xffffffffu ? amax : (int)s_u32[0];
-        if (p.kept_count) p.kept_count[b] = (int)run_kept;
+        p.out[b] = token == 0xffffffffu ? amax : (int)token;
+        if (p.kept_count) p.kept_count[b] = (int)kept;
     }
 }
 
@@ -477,7 +601,7 @@ int sd_sample_bonus(const void* logits, int logit_dtype, int64_t stride_b, int64
     p.kept_count = kept_count;
     // digits that cover every information bit of the order key: fp32 32, fp16 19 (1+8+10 after widening), bf16 16
     p.ndigits = logit_dtype == SD_F32 ? 4 : (logit_dtype == SD_F16 ? 3 : 2);
-    const size_t smem = (size_t)kSampWarps * kBins * (4 + 8);
+    const size_t smem = (size_t)kSampWarps * kBins * (4 + 8) + (size_t)kCompactCap * 8;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     cudaError_t e;
     if (logit_dtype == SD_F32) {

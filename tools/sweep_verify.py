@@ -72,6 +72,7 @@ def main():
     ap.add_argument("--pdl", type=int, default=1)
     ap.add_argument("--single-graphs", action="store_true", help="one graph per launch (no PDL edges)")
     ap.add_argument("--quick", action="store_true", help="few configurations")
+    ap.add_argument("--extras", action="store_true", help="sampling-mode verify and bonus sampler timings")
     ap.add_argument("--tma", action="store_true", help="only the TMA-ring verify variant sweep")
     ap.add_argument("--stats", action="store_true")
     args = ap.parse_args()
@@ -147,6 +148,47 @@ def main():
                                   "GBps": nb / us / 1e3, "bytes": nb, "mean_keep": mean_keep}), flush=True)
         cuda_ops.set_kv_variant(0)
         del arena, stages, tables
+
+    if args.extras:
+        # sampling-mode verify (softmax statistics in the same pass) and the bonus sampler
+        for mode in ("typical", "confidence", "topk"):
+            sts = []
+            for i in range(args.nbuf):
+                st = VerifyStep(B, K, V, arena=None, device=dev, logits_dtype=dt, mode=mode, threshold=5.0 if mode == "topk" else 0.3)
+                st.logits.copy_(steps[i].logits)
+                st.draft_ids.copy_(steps[i].draft_ids)
+                sts.append(st)
+            us = time_graphs([s.run for s in sts], args.iters)
+            print(json.dumps({"kernel": "verify_step", "mode": mode, "us": us, "GBps": nbytes / us / 1e3}), flush=True)
+            del sts
+        acc = torch.randint(0, K + 1, (B,), device=dev, dtype=torch.int32)
+        u = torch.rand(B, device=dev)
+        out = torch.empty(B, dtype=torch.int32, device=dev)
+        for name, kw in (("greedy", dict(uniform=None)), ("T0.7", dict(uniform=u, temperature=0.7)),
+                         ("T0.7_k50_p0.9 (reference default)", dict(uniform=u, temperature=0.7, top_k=50, top_p=0.9)),
+                         ("T0.7_p0.9", dict(uniform=u, temperature=0.7, top_p=0.9))):
+            us = time_graphs([lambda s=s: cuda_ops.sample_bonus_cuda(s.logits, row_index=acc, out=out, **kw) for s in steps], args.iters)
+            print(json.dumps({"kernel": "sample_bonus", "config": name, "us": us, "row_MB": B * V * steps[0].logits.element_size() / 1e6}), flush=True)
+        # the reference's per-sequence sampler on the same GPU rows (torch ops), for scale
+        def ref_sampler(s):
+            for b in range(B):
+                row = s.logits[b, int(0)] / 0.7
+                tk, ti = torch.topk(row, 50)
+                f = torch.full_like(row, float("-inf")).scatter_(-1, ti, tk)
+                sl, si = torch.sort(f, descending=True)
+                pr = torch.softmax(sl.float(), -1)
+                rm = torch.cumsum(pr, -1) > 0.9
+                rm[0] = False
+                f = f.masked_fill(rm.scatter(-1, si, rm), float("-inf"))
+                torch.multinomial(torch.softmax(f.float(), -1), 1)
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ref_sampler(steps[0])
+        torch.cuda.synchronize()
+        a.record()
+        ref_sampler(steps[1])
+        b2.record()
+        torch.cuda.synchronize()
+        print(json.dumps({"kernel": "torch per-sequence sampler (topk+sort+cumsum+multinomial x B)", "us": a.elapsed_time(b2) * 1e3}), flush=True)
 
     if not args.skip_attn:
         # one layer of verify attention per launch, rotating over `nl` layers of arena so KV comes from HBM
