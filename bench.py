@@ -50,6 +50,10 @@ def parse_args():
     ap.add_argument("--tuning", default="", help="threads,vectors_per_thread for the verify kernel (sweeps)")
     ap.add_argument("--kv-variant", type=int, default=0)
     ap.add_argument("--batch", type=int, default=CFG["B"], help="sequences per GPU")
+    ap.add_argument("--no-fuse", action="store_true", help="two launches per step (verify, kv_append) instead of sd_verify_append")
+    ap.add_argument("--interleave", action="store_true", help="fused launch: append CTAs of a sequence group right after its verify CTAs")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="kv_append waits for the whole verify grid (PDL) instead of per-sequence flags")
     ap.add_argument("--exchange", default="peer-kv", choices=["peer-kv", "peer", "nccl"],
                     help="N>1: fused peer-memory exchange in the verify kernel (default) or one NCCL all-gather per step")
     return ap.parse_args()
@@ -238,6 +242,8 @@ def run_ours(args):
         cuda_ops.set_verify_tuning(t, v)
     if args.kv_variant:
         cuda_ops.set_kv_variant(args.kv_variant)
+    if args.interleave:
+        cuda_ops._capi.lib().sd_verify_append_set_interleave(1)
 
     B, K, V, NB = args.batch, CFG["K"], CFG["V"], CFG["nbuf"]
     R = K + 1
@@ -285,15 +291,26 @@ def run_ours(args):
     def one_step(i, px=None):
         px = peer if px is None else px
         st = steps[i]
+        if not args.no_fuse:
+            # the whole step in ONE launch (sd_verify_append): verify CTAs, then append CTAs that wait per sequence
+            arena.layer_table = tables[i]
+            cuda_ops.verify_append_launch(st.logits, st.draft_ids, st.accept_len, st.accepted_mask, st.target_ids, st.bonus,
+                                          st.packed, st.workspace, st.seq_ready, arena, zero_rejected=True, exchange=px,
+                                          exchange_push_in_append=args.exchange == "peer-kv")
+            if exch is not None:
+                exch.all_gather(st.packed)
+            return
         push_in_kv = args.exchange == "peer-kv"
         st.exchange = None if push_in_kv else px
+        st.raise_flags = not args.no_overlap  # kv_append starts per sequence, overlapping the verify tail
         st.run()
         arena.layer_table = tables[i]
         # N>1, peer exchange: the records are pushed to every rank by the verify finalizers ("peer") or by the
         # first CTA of the append ("peer-kv": the NVLink round trip hides behind the append); the last CTA of
         # the append confirms + gathers them (no launch of its own)
         arena.append(st.accept_len, keep_bias=1, zero_rejected=True, check_capacity=False, exchange=px,
-                     exchange_packed=st.packed if (push_in_kv and px is not None) else None)
+                     exchange_packed=st.packed if (push_in_kv and px is not None) else None,
+                     seq_ready=st.seq_ready if st.raise_flags else None)
         if exch is not None:
             exch.all_gather(st.packed)
 
@@ -384,8 +401,9 @@ def run_ours(args):
         arena.layer_table = tables[i]
         arena.append(steps[i].accept_len, keep_bias=1, zero_rejected=True, check_capacity=False)
 
-    for st in steps:  # the kernel alone: without the peer stores (they need a matching wait on every rank)
+    for st in steps:  # the kernel alone: without the peer stores / per-sequence flags (both need the append after it)
         st.exchange = None
+        st.raise_flags = False
     verify_ms = isolate(lambda i: steps[i].run(), args.steps)
     for st in steps:
         st.exchange = peer
@@ -475,10 +493,11 @@ def run_ours(args):
             "config": workload_config(args, world),
             "tokens_per_step": tokens_per_step_all, "positions_per_s": B * world * R / (step_ms * 1e-3),
             "mean_accept_len": mean_keep - 1.0,
-            "gpu_launches": args.steps * 2,
-            "launches_per_step": {"sd_verify_kernel": 1, "sd_kv_append_kernel": 1,
+            "gpu_launches": args.steps * (2 if args.no_fuse else 1),
+            "launches_per_step": ({"sd_verify_kernel": 1, "sd_kv_append_kernel": 1} if args.no_fuse else {"sd_verify_append_kernel": 1}) | {
                                   "nccl_allgather": 1 if exch is not None else 0},
             "exchange": exchange_kind,
+            "verify_kv_overlap": "per-sequence flags (kv_append starts on a sequence as soon as it is verified)" if not args.no_overlap else "none (PDL only)",
             "pipelined_exchange": ({"lag_steps": 1, "ms_per_step": lag1_ms, "value": tokens_per_step_all / (lag1_ms * 1e-3),
                                     "note": "same step, but each append gathers the PREVIOUS step's records: ranks are not in lockstep; "
                                             "every rank still has its own shard's records immediately"} if lag1_ms > 0 else None),

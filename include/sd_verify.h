@@ -129,6 +129,10 @@ int sd_exchange_wait(const sd_exchange* exchange, int32_t* out, void* stream);
  * exchange    (nullable, device pointer) when set, the finalizer of sequence b also stores the packed
  *             record into row rank * rows_per_rank + b of every peer's exchange buffer (see above);
  *             requires width == K + 2 and B <= rows_per_rank
+ * seq_ready   (nullable) [B] int32, zero before the launch: flag b is raised (release) once every output
+ *             of sequence b is final.  Pass the same array to the sd_kv_append call that follows on the
+ *             stream: its CTAs then start on sequence b as soon as b is verified instead of waiting
+ *             for the whole verify grid, and its last CTA re-zeroes the flags.
  * workspace   sd_verify_workspace_bytes(B, rows) bytes, 8-byte aligned, zeroed once with sd_verify_workspace_init;
  *             the kernel leaves it zeroed again, so one init serves any number of launches
  *             (including graph replays).  Must not be shared by launches that may overlap.
@@ -142,7 +146,8 @@ int sd_verify_prefix(const void* logits, int logit_dtype, int64_t stride_b, int6
                      const void* draft_ids, int id_dtype, int64_t id_stride_b,
                      int32_t* accept_len, uint8_t* accepted_mask, int32_t* target_ids,
                      int32_t* bonus, int32_t* packed, void* workspace, size_t workspace_bytes,
-                     int B, int rows, int K, int V, void* stream, const sd_exchange* exchange);
+                     int B, int rows, int K, int V, void* stream, const sd_exchange* exchange,
+                     int32_t* seq_ready);
 
 /*
  * Same pass with softmax statistics ("sampling mode"): one read of the logits yields, per row,
@@ -164,7 +169,7 @@ int sd_verify_step(const void* logits, int logit_dtype, int64_t stride_b, int64_
                    uint8_t* accepted_mask, int32_t* target_ids, int32_t* bonus, int32_t* packed,
                    float* token_prob, float* row_max, float* row_sumexp, void* workspace,
                    size_t workspace_bytes, int B, int rows, int K, int V, void* stream,
-                   const sd_exchange* exchange);
+                   const sd_exchange* exchange, int32_t* seq_ready);
 
 /* Tuning hook used by tools/ and bench.py sweeps: threads per CTA (128..1024, multiple of 32),
  * 16-byte vectors in flight per thread (1..16), 0 restores the built-in heuristic. */
@@ -229,6 +234,12 @@ typedef struct sd_kv_layer {
  *             (written by the verify launch): when set, the first CTA of this launch pushes them to
  *             every peer at its start -- the NVLink round trip then hides behind the append -- and
  *             the verify launch must be issued WITHOUT `exchange`.
+ * seq_ready   (nullable) the flag array given to the sd_verify_* launch just before on the stream (n_keep
+ *             must be that launch's accept_len; column kernel only, i.e. unmasked 16-byte aligned rows,
+ *             else SD_ERR_UNSUPPORTED).  The launch then does NOT wait for the whole verify grid: every
+ *             thread waits for its own sequence's flag, so the append of early sequences overlaps the
+ *             verification of late ones; the last CTA waits for the verify grid, re-zeroes the flags
+ *             and commits the lengths.
  * rows_ready_early  non-zero = the caller guarantees that the layer table and the offered rows were
  *             written at least two kernels before this call on the stream (in the verify step they
  *             come from the target forward; the kernel just before this one is the fused verify,
@@ -246,7 +257,7 @@ int sd_kv_append(const sd_kv_layer* layers, int n_layers, int B, int H, int R, i
                  int keep_bias, const uint8_t* accepted_mask, int zero_rejected,
                  int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, int rows_ready_early,
                  void* stream, const sd_exchange* exchange, int32_t* exchange_out,
-                 const int32_t* exchange_packed);
+                 const int32_t* exchange_packed, int32_t* seq_ready);
 
 /*
  * Single-layer form with the layer record passed by value and a uniform current length
@@ -260,6 +271,51 @@ int sd_kv_append_layer(void* arena_k, void* arena_v, const void* new_k, const vo
                        int64_t arena_stride_h, int64_t new_stride_b, int64_t new_stride_h,
                        int64_t new_stride_r, int64_t base_len, const int32_t* n_keep, int keep_bias,
                        const uint8_t* accepted_mask, int zero_rejected, int32_t* ticket, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The whole verify step in ONE launch: fused verify (greedy) + kv_append of all layers.
+ *
+ * Same results as sd_verify_prefix(rows = K + 1, seq_ready) followed by sd_kv_append(n_keep =
+ * accept_len, keep_bias = 1, seq_lens in place, seq_ready), i.e. the reference's per-sequence
+ * accept / bonus / append block (src/specdec/core/pipeline.py:2958-3620 for the arithmetic part) --
+ * but the append CTAs are part of the verify grid (dispatched after the verify CTAs, waiting on the
+ * per-sequence flags), so a step pays one launch, one ramp and one tail instead of two.
+ * Requirements: greedy acceptance, unmasked 16-byte aligned KV rows (the column kernel), the
+ * bulk-chunk verify variant (the default).  Otherwise SD_ERR_UNSUPPORTED: issue the two launches.
+ */
+typedef struct sd_step_args {
+    /* fused verify: see sd_verify_prefix */
+    const void* logits;
+    int32_t logit_dtype, id_dtype;
+    int64_t stride_b, stride_r, id_stride_b;
+    const void* draft_ids;
+    int32_t* accept_len;
+    uint8_t* accepted_mask; /* nullable */
+    int32_t* target_ids;    /* nullable */
+    int32_t* bonus;         /* nullable */
+    int32_t* packed;        /* nullable (required when exchange_push_in_append) */
+    void* workspace;
+    size_t workspace_bytes;
+    int32_t B, rows, K, V;
+    /* kv_append of the rows == K + 1 offered rows: see sd_kv_append */
+    const sd_kv_layer* layers;
+    int32_t n_layers, H, zero_rejected, exchange_push_in_append;
+    int64_t row_bytes, capacity, arena_stride_b, arena_stride_h, new_stride_b, new_stride_h, new_stride_r;
+    int64_t max_seq_len_host;
+    int32_t* seq_lens;      /* updated in place */
+    int32_t* overflow_flag; /* nullable */
+    int32_t* ticket;
+    int32_t* seq_ready;     /* [B] int32, zero before the launch, re-zeroed by it */
+    /* multi-GPU exchange (nullable) */
+    const sd_exchange* exchange;
+    int32_t* exchange_out;
+} sd_step_args;
+
+int sd_verify_append(const sd_step_args* args, void* stream);
+/* Evidence runs: 0 (default) = all append CTAs after all verify CTAs; 1 = the append CTAs of a group of
+ * sequences directly follow that group's verify CTAs in block order.  Measured on B200 the interleaved
+ * order is slower (43 vs 34 us per step): the waiting append CTAs hold registers the verify CTAs need. */
+int sd_verify_append_set_interleave(int enabled);
 
 /* Variant selector for sd_kv_append (evidence runs): 0 = heuristic, 1 = 128-bit LDG/STG kernel,
  * 2 = cp.async.bulk (TMA 1-D) shared-memory staged kernel, 3 = column kernel (one thread per 16-byte

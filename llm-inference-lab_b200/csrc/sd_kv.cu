@@ -14,86 +14,12 @@
 //   2  "bulk": one thread per (layer, K|V, b, h) unit issues ONE cp.async.bulk (TMA 1-D)
 //              global->shared load of the accepted rows and ONE shared->global bulk store of the R
 //              offered slots (accepted rows followed by zeros) -- no per-element instructions.
-#include "sd_common.cuh"
+#include "sd_kv_col.cuh"
 
 namespace sd {
 
 static int g_kv_variant = 0;
 static int g_kv_rows_in_flight = 0;  // column kernel: rows per load batch (0 = heuristic)
-
-struct KvParams {
-    const sd_kv_layer* layers;  // device table, or nullptr -> `single` (passed by value)
-    sd_kv_layer single;
-    int64_t base_len;           // uniform length added to seq_lens[b] (functional single-layer form)
-    int n_layers, B, H, R;
-    int64_t row_bytes, capacity;
-    int64_t arena_stride_b, arena_stride_h;
-    int64_t new_stride_b, new_stride_h, new_stride_r;
-    const int32_t* seq_lens;
-    int32_t* seq_lens_out;
-    const int32_t* n_keep;
-    int keep_bias;
-    const uint8_t* mask;
-    int zero_rejected;
-    int early_rows;  // column kernel: fetch the offered rows before griddepcontrol.wait
-    int32_t* overflow;
-    int32_t* ticket;
-    const sd_exchange* xchg;  // nullable: confirm + gather the verify records of this step (last CTA)
-    int32_t* xchg_out;
-    const int32_t* xchg_packed;  // nullable: this launch also PUSHES the local records (first CTA, at its start)
-    unsigned total_ctas;
-};
-
-SD_DEVINL int keep_count(const KvParams& p, int b) {
-    int n = p.R;
-    if (p.n_keep) {
-        n = p.n_keep[b] + p.keep_bias;
-        n = n < 0 ? 0 : (n > p.R ? p.R : n);
-    }
-    return n;
-}
-
-// position of the j-th set bit of mask[b, 0..R) (reference.py:149-157), or -1
-SD_DEVINL int masked_source_row(const uint8_t* mask, int b, int R, int j) {
-    int seen = 0;
-    for (int k = 0; k < R; ++k) {
-        if (mask[(int64_t)b * R + k]) {
-            if (seen == j) return k;
-            ++seen;
-        }
-    }
-    return -1;
-}
-
-// last CTA to retire publishes the new lengths (so seq_lens_out may alias seq_lens)
-SD_DEVINL void retire_and_commit(const KvParams& p) {
-    __shared__ int s_last;
-    // The ticket orders every CTA's READS of seq_lens / n_keep (complete once their values have been
-    // consumed, i.e. before this barrier) ahead of the length commit; the row stores themselves need
-    // no fence -- stream order publishes them to the next kernel.
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned prev = atomicAdd(reinterpret_cast<unsigned*>(p.ticket), 1u);
-        s_last = prev == p.total_ctas - 1u;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    if (p.seq_lens_out) {
-        for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
-            int len = (p.seq_lens ? p.seq_lens[b] : 0) + (int)p.base_len;
-            int n = keep_count(p, b);
-            if (p.mask) {  // cannot keep more rows than the mask offers
-                int bits = 0;
-                for (int k = 0; k < p.R; ++k) bits += p.mask[(int64_t)b * p.R + k] != 0;
-                n = n < bits ? n : bits;
-            }
-            if ((int64_t)len + n > p.capacity) n = (int)(p.capacity - len > 0 ? p.capacity - len : 0);
-            p.seq_lens_out[b] = len + n;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *p.ticket = 0;
-}
 
 template <typename VecT>
 __global__ void __launch_bounds__(256) kv_append_vec_kernel(const KvParams p) {
@@ -153,93 +79,11 @@ __global__ void __launch_bounds__(256) kv_append_vec_kernel(const KvParams p) {
     retire_and_commit(p);
 }
 
-// ---- variant 3 "column": one thread owns one 16-byte column of a (layer, b, h) for ALL R offered
-// rows of K and V: up to 2*RB independent 128-bit loads in flight per thread, issued before the first
-// store, and R-times fewer threads than variant 1 (one wave instead of four).
+// ---- variant 3 "column" (body in sd_kv_col.cuh) ----
 template <int RB>
 __global__ void __launch_bounds__(256) kv_append_col_kernel(const KvParams p) {
-    const int layer = blockIdx.y;
-    const int vpr = (int)(p.row_bytes >> 4);
-    const int64_t slots = (int64_t)p.B * p.H * vpr;
-    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = slot < slots;
-    int v = 0, h = 0, b = 0;
-    sd_kv_layer L{nullptr, nullptr, nullptr, nullptr};
-    const char* sk = nullptr;
-    const char* sv = nullptr;
-    uint4 kx[RB], vx[RB];
-    // early_rows: the offered rows (and the layer table) were produced at least two kernels ago -- in
-    // the verify step they come from the target forward, and the kernel just before this one is the
-    // fused verify, which only writes accept_len -- so the first RB rows are fetched BEFORE
-    // griddepcontrol.wait, while the previous kernel drains.  Only seq_lens / n_keep wait.
-    if (p.early_rows && active) {
-        v = (int)(slot % vpr);
-        const int64_t t = slot / vpr;
-        h = (int)(t % p.H);
-        b = (int)(t / p.H);
-        L = p.layers ? p.layers[layer] : p.single;
-        sk = reinterpret_cast<const char*>(L.new_k) + (int64_t)b * p.new_stride_b + (int64_t)h * p.new_stride_h + ((int64_t)v << 4);
-        sv = reinterpret_cast<const char*>(L.new_v) + (int64_t)b * p.new_stride_b + (int64_t)h * p.new_stride_h + ((int64_t)v << 4);
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-            if (u < p.R) {
-                kx[u] = ldg_stream_v4(sk + (int64_t)u * p.new_stride_r);
-                vx[u] = ldg_stream_v4(sv + (int64_t)u * p.new_stride_r);
-            }
-        }
-    }
-    pdl_wait();
     pdl_trigger();
-    if (p.xchg && p.xchg_packed && blockIdx.x == 0 && blockIdx.y == 0) exchange_push_cta(p.xchg, p.xchg_packed, p.B);
-    if (active) {
-        if (!p.early_rows) {
-            v = (int)(slot % vpr);
-            const int64_t t = slot / vpr;
-            h = (int)(t % p.H);
-            b = (int)(t / p.H);
-            L = p.layers ? p.layers[layer] : p.single;
-            sk = reinterpret_cast<const char*>(L.new_k) + (int64_t)b * p.new_stride_b + (int64_t)h * p.new_stride_h + ((int64_t)v << 4);
-            sv = reinterpret_cast<const char*>(L.new_v) + (int64_t)b * p.new_stride_b + (int64_t)h * p.new_stride_h + ((int64_t)v << 4);
-        }
-        const int len = (p.seq_lens ? p.seq_lens[b] : 0) + (int)p.base_len;
-        int n = keep_count(p, b);
-        int room = (int)(p.capacity - len);
-        room = room < 0 ? 0 : (room > p.R ? p.R : room);
-        if (n > room) {
-            if (p.overflow) *p.overflow = 1;
-            n = room;
-        }
-        const int nstore = p.zero_rejected ? room : n;
-        const int64_t doff = (int64_t)b * p.arena_stride_b + (int64_t)h * p.arena_stride_h + (int64_t)len * p.row_bytes + ((int64_t)v << 4);
-        char* dk = reinterpret_cast<char*>(L.arena_k) + doff;
-        char* dv = reinterpret_cast<char*>(L.arena_v) + doff;
-        for (int j0 = 0; j0 < nstore; j0 += RB) {
-            if (!(p.early_rows && j0 == 0)) {
-#pragma unroll
-                for (int u = 0; u < RB; ++u) {
-                    const int j = j0 + u;
-                    if (j < n) {
-                        kx[u] = ldg_stream_v4(sk + (int64_t)j * p.new_stride_r);
-                        vx[u] = ldg_stream_v4(sv + (int64_t)j * p.new_stride_r);
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < RB; ++u) {
-                const int j = j0 + u;
-                if (j < nstore) {
-                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                    *reinterpret_cast<uint4*>(dk + (int64_t)j * p.row_bytes) = j < n ? kx[u] : z;
-                    *reinterpret_cast<uint4*>(dv + (int64_t)j * p.row_bytes) = j < n ? vx[u] : z;
-                }
-            }
-        }
-    }
-    // Fused result exchange (multi-GPU): CTA (0,0) -- which pushed this rank's records at its start when
-    // exchange_packed is set -- gathers every rank's records of the epoch once its own rows are copied:
-    // the NVLink round trips overlap the rest of the append instead of trailing it.
-    if (p.xchg && blockIdx.x == 0 && blockIdx.y == 0) exchange_gather_cta(p.xchg, p.xchg_out);
-    retire_and_commit(p);
+    kv_col_body<RB>(p, (int)blockIdx.x, (int)blockIdx.y);
 }
 
 // ---- cp.async.bulk (TMA 1-D) variant -------------------------------------------------------------
@@ -350,6 +194,54 @@ static bool aligned_to(const KvParams& p, const sd_kv_layer* host_layers, int n_
     return true;
 }
 
+
+int kv_prepare_col(const sd_kv_layer* layers, int n_layers, int B, int H, int R, int64_t row_bytes, int64_t capacity,
+                   int64_t arena_stride_b, int64_t arena_stride_h, int64_t new_stride_b, int64_t new_stride_h,
+                   int64_t new_stride_r, const int32_t* seq_lens, int32_t* seq_lens_out, const int32_t* n_keep,
+                   int keep_bias, int zero_rejected, int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket,
+                   const sd_exchange* exchange, int32_t* exchange_out, const int32_t* exchange_packed, int32_t* seq_ready,
+                   KvParams* out, unsigned* grid_x, int* rb) {
+    if (n_layers <= 0 || B <= 0 || H <= 0 || R <= 0 || row_bytes <= 0 || capacity < 0 || !layers || !ticket) return SD_ERR_INVALID_ARG;
+    if (max_seq_len_host >= 0 && max_seq_len_host + R > capacity) return SD_ERR_CAPACITY;
+    KvParams p;
+    p.layers = layers;
+    p.single = sd_kv_layer{nullptr, nullptr, nullptr, nullptr};
+    p.base_len = 0;
+    p.n_layers = n_layers;
+    p.B = B;
+    p.H = H;
+    p.R = R;
+    p.row_bytes = row_bytes;
+    p.capacity = capacity;
+    p.arena_stride_b = arena_stride_b;
+    p.arena_stride_h = arena_stride_h;
+    p.new_stride_b = new_stride_b;
+    p.new_stride_h = new_stride_h;
+    p.new_stride_r = new_stride_r;
+    p.seq_lens = seq_lens;
+    p.seq_lens_out = seq_lens_out;
+    p.n_keep = n_keep;
+    p.keep_bias = keep_bias;
+    p.mask = nullptr;
+    p.zero_rejected = zero_rejected;
+    p.early_rows = 0;
+    p.overflow = overflow_flag;
+    p.ticket = ticket;
+    p.xchg = exchange;
+    p.xchg_out = exchange_out;
+    p.xchg_packed = exchange_packed;
+    p.seq_ready = seq_ready;
+    p.fused = 1;
+    if (!aligned_to(p, nullptr, 0, 16)) return SD_ERR_UNSUPPORTED;
+    const int64_t slots = (int64_t)B * H * (row_bytes / 16);
+    *grid_x = (unsigned)((slots + 255) / 256);
+    p.total_ctas = *grid_x * (unsigned)n_layers;
+    int r = R <= 6 ? R : ((R + 1) / 2 <= 6 ? (R + 1) / 2 : 6);
+    *rb = r;
+    *out = p;
+    return SD_OK;
+}
+
 }  // namespace sd
 
 extern "C" {
@@ -371,7 +263,7 @@ static int kv_append_impl(const sd_kv_layer* layers, const sd_kv_layer* single, 
                           const int32_t* n_keep, int keep_bias, const uint8_t* accepted_mask, int zero_rejected,
                           int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, int early_rows, void* stream,
                           const sd_exchange* exchange = nullptr, int32_t* exchange_out = nullptr,
-                          const int32_t* exchange_packed = nullptr) {
+                          const int32_t* exchange_packed = nullptr, int32_t* seq_ready = nullptr) {
     using namespace sd;
     if (n_layers < 0 || B < 0 || H < 0 || R < 0 || row_bytes <= 0 || capacity < 0) return SD_ERR_INVALID_ARG;
     if (n_layers == 0 || B == 0 || H == 0) return SD_OK;
@@ -408,6 +300,8 @@ static int kv_append_impl(const sd_kv_layer* layers, const sd_kv_layer* single, 
     p.xchg = exchange;
     p.xchg_out = exchange_out;
     p.xchg_packed = exchange_packed;
+    p.seq_ready = seq_ready;
+    p.fused = 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
     if (R == 0) {  // nothing offered: only the length commit (identity) is required
@@ -425,6 +319,7 @@ static int kv_append_impl(const sd_kv_layer* layers, const sd_kv_layer* single, 
     if (variant == 0) variant = col_ok ? 3 : 1;
     if (variant == 2 && !bulk_ok) variant = 1;
     if (variant == 3 && !col_ok) variant = 1;
+    if (seq_ready && (variant != 3 || !n_keep)) return SD_ERR_UNSUPPORTED;  // the per-sequence wait lives in the column kernel
 
     if (variant == 3) {
         const int64_t slots = (int64_t)B * H * (row_bytes / 16);
@@ -474,13 +369,14 @@ int sd_kv_append(const sd_kv_layer* layers, int n_layers, int B, int H, int R, i
                  int64_t new_stride_h, int64_t new_stride_r, const int32_t* seq_lens, int32_t* seq_lens_out,
                  const int32_t* n_keep, int keep_bias, const uint8_t* accepted_mask, int zero_rejected,
                  int64_t max_seq_len_host, int32_t* overflow_flag, int32_t* ticket, int rows_ready_early, void* stream,
-                 const sd_exchange* exchange, int32_t* exchange_out, const int32_t* exchange_packed) {
+                 const sd_exchange* exchange, int32_t* exchange_out, const int32_t* exchange_packed,
+                 int32_t* seq_ready) {
     if (n_layers > 0 && !layers) return SD_ERR_INVALID_ARG;
     if (exchange && (n_layers == 0 || B == 0 || H == 0 || R == 0)) return SD_ERR_UNSUPPORTED;  // nothing would launch
     return kv_append_impl(layers, nullptr, 0, n_layers, B, H, R, row_bytes, capacity, arena_stride_b, arena_stride_h,
                           new_stride_b, new_stride_h, new_stride_r, seq_lens, seq_lens_out, n_keep, keep_bias,
                           accepted_mask, zero_rejected, max_seq_len_host, overflow_flag, ticket, rows_ready_early, stream,
-                          exchange, exchange_out, exchange_packed);
+                          exchange, exchange_out, exchange_packed, seq_ready);
 }
 
 int sd_kv_append_layer(void* arena_k, void* arena_v, const void* new_k, const void* new_v, int B, int H, int R,

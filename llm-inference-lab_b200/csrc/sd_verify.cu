@@ -30,7 +30,7 @@
 // Exact torch.argmax semantics (first maximal index; NaN maximal, first NaN; -0 == +0) are kept
 // by (a) canonical-NaN propagating max, (b) folding -0 to +0 once per vector, (c) tie-breaking
 // every reduction level on the smallest position.
-#include "sd_common.cuh"
+#include "sd_kv_col.cuh"
 
 namespace sd {
 
@@ -74,6 +74,7 @@ struct VerifyParams {
     float threshold, scale_log2;  // scale_log2 = inv_temperature * log2(e)
     float inv_temperature;
     const sd_exchange* xchg;    // nullable: peer-memory result exchange (device memory)
+    int32_t* seq_ready;         // nullable: flag b is raised once sequence b's outputs are final
     unsigned long long* trace;  // evidence runs: [grid][4] = {globaltimer at entry, after the scan, at exit, smid}
 };
 
@@ -506,6 +507,15 @@ SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int n
             }
         }
     }
+    if (wid == 0 && p.seq_ready) {
+        // per-sequence completion flag: lets the kv_append launch that follows start on sequence b while other
+        // sequences are still being verified (sd_kv_append, seq_ready)
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(p.seq_ready + b), "r"(1) : "memory");
+        }
+    }
     cta_sync<NAMED>(nthreads);  // s_tgt and the reduce scratch are reused by the caller's next segment
 }
 
@@ -737,18 +747,8 @@ __global__ void __launch_bounds__(kTmaConsumers + 32) verify_tma_kernel(const Ve
 // All of a CTA's bytes are in flight after one instruction, independent of register allocation, and
 // several CTAs per SM overlap each other's wait / fold / publish phases.
 template <typename T, bool STATS>
-__global__ void __launch_bounds__(256) verify_bulk_kernel(const VerifyParams p) {
-    extern __shared__ __align__(128) unsigned char stage[];
-    __shared__ __align__(8) uint64_t bar;
+SD_DEVINL void verify_bulk_body(const VerifyParams& p, const int unit, unsigned char* stage, uint64_t* bar) {
     const int tid = threadIdx.x, nthreads = blockDim.x;
-    if (tid == 0) {
-        vbar_init(&bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    pdl_wait();
-    pdl_trigger();
-    const int unit = blockIdx.x;
     const int chunk = unit % p.S;
     const int row = unit / p.S;
     const int it0 = chunk * p.units_per_chunk;
@@ -761,10 +761,10 @@ __global__ void __launch_bounds__(256) verify_bulk_kernel(const VerifyParams p) 
     nv = nv < 0 ? 0 : (nv > cap ? cap : nv);
     if (tid == 0) {
         if (nv > 0) {
-            vbar_arrive_expect_tx(&bar, (unsigned)nv * 16u);
-            vbulk_g2s(stage, g.vp + v0, (unsigned)nv * 16u, &bar);
+            vbar_arrive_expect_tx(bar, (unsigned)nv * 16u);
+            vbulk_g2s(stage, g.vp + v0, (unsigned)nv * 16u, bar);
         } else {
-            vbar_arrive(&bar);
+            vbar_arrive(bar);
         }
     }
     ThreadAcc<T, STATS> acc;
@@ -772,12 +772,63 @@ __global__ void __launch_bounds__(256) verify_bulk_kernel(const VerifyParams p) 
     if constexpr (STATS) {  // overlaps the bulk copy
         if (p.mode == SD_ACCEPT_TOPK) acc.count_above(draft_logit<T>(p, g, row));
     }
-    vbar_wait(&bar, 0u);
+    vbar_wait(bar, 0u);
     const uint4* src = reinterpret_cast<const uint4*>(stage);
 #pragma unroll 4
     for (int k = tid; k < nv; k += nthreads) acc.add(src[k], v0 + k, true, p.scale_log2);
     if (publish_segment<T, STATS, false>(p, g, acc, row, it0, it1, chunk, tid, nthreads))
         finalize_sequence<T, STATS, false>(p, row / p.rows, p.S, tid, nthreads);
+}
+
+template <typename T, bool STATS>
+__global__ void __launch_bounds__(256) verify_bulk_kernel(const VerifyParams p) {
+    extern __shared__ __align__(128) unsigned char stage[];
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+        vbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_wait();
+    pdl_trigger();
+    verify_bulk_body<T, STATS>(p, (int)blockIdx.x, stage, &bar);
+}
+
+// ---- the whole step in ONE launch: fused verify + kv_append ------------------------------------------
+// CTAs [0, n_verify) run the bulk-chunk verify body; CTAs [n_verify, n_verify + kv_gx * layers) run the
+// kv_append column body for (x, layer), each thread waiting for its sequence's completion flag (raised
+// by the verify finalizer, sd_kv_col.cuh).  Blocks are dispatched in index order, so append CTAs become
+// resident only when every verify CTA has started; they wait on flags, verify CTAs wait on nothing that
+// an append CTA produces -> no deadlock.  One launch overhead, one ramp and one tail per step instead of two.
+template <typename T, int RB>
+__global__ void __launch_bounds__(256) verify_append_kernel(const VerifyParams vp, const KvParams kp, const int n_verify,
+                                                            const int kv_gx, const int interleave_group) {
+    extern __shared__ __align__(128) unsigned char stage[];
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+        vbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_wait();
+    pdl_trigger();
+    if (interleave_group > 0) {
+        // Interleaved order: the append CTAs of a group of sequences come right after that group's verify CTAs,
+        // so they are dispatched in the middle of the grid, wait about one CTA lifetime for their flags and
+        // move their rows while later sequences are still being verified (no serialised append phase).
+        // group = verify_per_group verify CTAs + kp.n_layers append CTAs (one kv x-slot, every layer).
+        const int g = (int)blockIdx.x / interleave_group, r = (int)blockIdx.x - g * interleave_group;
+        const int verify_per_group = interleave_group - kp.n_layers;
+        if (r < verify_per_group) verify_bulk_body<T, false>(vp, g * verify_per_group + r, stage, &bar);
+        else kv_col_body<RB>(kp, g, r - verify_per_group);
+        return;
+    }
+    if ((int)blockIdx.x < n_verify) {
+        verify_bulk_body<T, false>(vp, (int)blockIdx.x, stage, &bar);
+    } else {
+        const int cta = (int)blockIdx.x - n_verify;
+        kv_col_body<RB>(kp, cta % kv_gx, cta / kv_gx);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -848,6 +899,43 @@ static cudaError_t launch_bulk_t(const VerifyParams& p, unsigned grid, int threa
     return launch_kernel(verify_bulk_kernel<T, STATS>, dim3(grid), dim3(threads), smem, st, p);
 }
 
+static int g_fused_interleave = 0;  // evidence runs: 1 = append CTAs of a sequence group right after its verify CTAs (measured slower: 43 vs 34 us)
+
+template <typename T, int RB>
+static cudaError_t launch_fused_t(const VerifyParams& p, const KvParams& kp, unsigned total, int n_verify, int kv_gx,
+                                  int threads, size_t smem, cudaStream_t st) {
+    // interleaving needs whole sequences per append x-slot and whole groups: n_verify = kv_gx * verify_per_group
+    int group = 0;
+    if (g_fused_interleave && kv_gx > 0 && n_verify % kv_gx == 0) {
+        const long long threads_per_seq = (long long)kp.H * (kp.row_bytes / 16);
+        if (threads_per_seq > 0 && 256 % threads_per_seq == 0 && ((long long)kp.B * threads_per_seq) % 256 == 0)
+            group = n_verify / kv_gx + kp.n_layers;
+    }
+    cudaError_t e = cudaFuncSetAttribute(verify_append_kernel<T, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return launch_kernel(verify_append_kernel<T, RB>, dim3(total), dim3(threads), smem, st, p, kp, n_verify, kv_gx, group);
+}
+
+template <typename T>
+static cudaError_t launch_fused_rb(const VerifyParams& p, const KvParams& kp, int rb, unsigned total, int n_verify, int kv_gx,
+                                   int threads, size_t smem, cudaStream_t st) {
+    switch (rb) {
+        case 1: return launch_fused_t<T, 1>(p, kp, total, n_verify, kv_gx, threads, smem, st);
+        case 2: return launch_fused_t<T, 2>(p, kp, total, n_verify, kv_gx, threads, smem, st);
+        case 3: return launch_fused_t<T, 3>(p, kp, total, n_verify, kv_gx, threads, smem, st);
+        case 4: return launch_fused_t<T, 4>(p, kp, total, n_verify, kv_gx, threads, smem, st);
+        case 5: return launch_fused_t<T, 5>(p, kp, total, n_verify, kv_gx, threads, smem, st);
+        default: return launch_fused_t<T, 6>(p, kp, total, n_verify, kv_gx, threads, smem, st);
+    }
+}
+
+static cudaError_t launch_fused(const VerifyParams& p, const KvParams& kp, int logit_dtype, int rb, unsigned total,
+                                int n_verify, int kv_gx, int threads, size_t smem, cudaStream_t st) {
+    if (logit_dtype == SD_F32) return launch_fused_rb<float>(p, kp, rb, total, n_verify, kv_gx, threads, smem, st);
+    if (logit_dtype == SD_F16) return launch_fused_rb<__half>(p, kp, rb, total, n_verify, kv_gx, threads, smem, st);
+    return launch_fused_rb<__nv_bfloat16>(p, kp, rb, total, n_verify, kv_gx, threads, smem, st);
+}
+
 // resident CTAs per SM of the persistent kernel for (T, vpt, stats, threads); cached per combination
 template <typename T, bool STATS>
 static int persist_occupancy_t(int vpt, int threads) {
@@ -885,7 +973,8 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
                       float inv_temperature, int32_t* accept_len, uint8_t* accepted_mask,
                       int32_t* target_ids, int32_t* bonus, int32_t* packed, float* token_prob,
                       float* row_max, float* row_sumexp, void* workspace, size_t workspace_bytes, int B,
-                      int rows, int K, int V, void* stream, const sd_exchange* exchange) {
+                      int rows, int K, int V, void* stream, const sd_exchange* exchange, int32_t* seq_ready,
+                      const KvParams* fused_kv = nullptr, unsigned fused_gx = 0, int fused_rb = 0) {
     if (B < 0 || K < 0 || V <= 0 || rows <= 0) return SD_ERR_INVALID_ARG;
     if (rows != K && rows != K + 1) return SD_ERR_SHAPE;
     if (rows > 64) return SD_ERR_UNSUPPORTED;
@@ -968,6 +1057,7 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
     p.scale_log2 = inv_temperature * 1.4426950408889634f;
     p.trace = nullptr;
     p.xchg = exchange;
+    p.seq_ready = seq_ready;
 
     unsigned grid;
     int tma_stages = 0;
@@ -1014,6 +1104,12 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
     if (variant == 0 && g_trace && (size_t)grid <= g_trace_ctas) p.trace = g_trace;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     cudaError_t e;
+    if (fused_kv) {
+        if (variant != 3 || stats) return SD_ERR_UNSUPPORTED;
+        const size_t smem = (size_t)p.units_per_chunk * threads * 16;
+        const unsigned total = grid + fused_gx * (unsigned)fused_kv->n_layers;
+        return to_status(launch_fused(p, *fused_kv, logit_dtype, fused_rb, total, (int)grid, (int)fused_gx, threads, smem, st));
+    }
     if (variant == 3) {
         const size_t smem = (size_t)p.units_per_chunk * threads * 16;
         if (stats) {
@@ -1095,10 +1191,35 @@ int sd_verify_prefix(const void* logits, int logit_dtype, int64_t stride_b, int6
                      const void* draft_ids, int id_dtype, int64_t id_stride_b, int32_t* accept_len,
                      uint8_t* accepted_mask, int32_t* target_ids, int32_t* bonus, int32_t* packed,
                      void* workspace, size_t workspace_bytes, int B, int rows, int K, int V, void* stream,
-                     const sd_exchange* exchange) {
+                     const sd_exchange* exchange, int32_t* seq_ready) {
     return sd::run_verify(false, logits, logit_dtype, stride_b, stride_r, draft_ids, id_dtype, id_stride_b,
                           SD_ACCEPT_GREEDY, 0.f, 1.f, accept_len, accepted_mask, target_ids, bonus, packed,
-                          nullptr, nullptr, nullptr, workspace, workspace_bytes, B, rows, K, V, stream, exchange);
+                          nullptr, nullptr, nullptr, workspace, workspace_bytes, B, rows, K, V, stream, exchange, seq_ready);
+}
+
+int sd_verify_append_set_interleave(int enabled) {
+    sd::g_fused_interleave = enabled ? 1 : 0;
+    return SD_OK;
+}
+
+int sd_verify_append(const sd_step_args* a, void* stream) {
+    using namespace sd;
+    if (!a) return SD_ERR_INVALID_ARG;
+    if (a->rows != a->K + 1) return SD_ERR_SHAPE;  // the append keeps accept_len + 1 of the K + 1 offered rows
+    if (!a->seq_ready || !a->accept_len) return SD_ERR_INVALID_ARG;
+    if (a->B <= 0) return SD_OK;
+    KvParams kp;
+    unsigned gx = 0;
+    int rb = 0;
+    int rc = kv_prepare_col(a->layers, a->n_layers, a->B, a->H, a->rows, a->row_bytes, a->capacity, a->arena_stride_b,
+                            a->arena_stride_h, a->new_stride_b, a->new_stride_h, a->new_stride_r, a->seq_lens, a->seq_lens,
+                            a->accept_len, 1, a->zero_rejected, a->max_seq_len_host, a->overflow_flag, a->ticket, a->exchange,
+                            a->exchange_out, a->exchange_push_in_append ? a->packed : nullptr, a->seq_ready, &kp, &gx, &rb);
+    if (rc != SD_OK) return rc;
+    return run_verify(false, a->logits, a->logit_dtype, a->stride_b, a->stride_r, a->draft_ids, a->id_dtype, a->id_stride_b,
+                      SD_ACCEPT_GREEDY, 0.f, 1.f, a->accept_len, a->accepted_mask, a->target_ids, a->bonus, a->packed, nullptr,
+                      nullptr, nullptr, a->workspace, a->workspace_bytes, a->B, a->rows, a->K, a->V, stream,
+                      a->exchange_push_in_append ? nullptr : a->exchange, a->seq_ready, &kp, gx, rb);
 }
 
 int sd_verify_step(const void* logits, int logit_dtype, int64_t stride_b, int64_t stride_r,
@@ -1106,11 +1227,11 @@ int sd_verify_step(const void* logits, int logit_dtype, int64_t stride_b, int64_
                    float inv_temperature, int32_t* accept_len, uint8_t* accepted_mask, int32_t* target_ids,
                    int32_t* bonus, int32_t* packed, float* token_prob, float* row_max, float* row_sumexp,
                    void* workspace, size_t workspace_bytes, int B, int rows, int K, int V, void* stream,
-                   const sd_exchange* exchange) {
+                   const sd_exchange* exchange, int32_t* seq_ready) {
     if (!(inv_temperature > 0.f)) return SD_ERR_INVALID_ARG;
     return sd::run_verify(true, logits, logit_dtype, stride_b, stride_r, draft_ids, id_dtype, id_stride_b, mode,
                           threshold, inv_temperature, accept_len, accepted_mask, target_ids, bonus, packed,
-                          token_prob, row_max, row_sumexp, workspace, workspace_bytes, B, rows, K, V, stream, exchange);
+                          token_prob, row_max, row_sumexp, workspace, workspace_bytes, B, rows, K, V, stream, exchange, seq_ready);
 }
 
 }  // extern "C"

@@ -35,9 +35,11 @@ SIGNATURES = {
     "sd_verify_workspace_bytes": (_sz, [_i, _i]),
     "sd_verify_workspace_init": (_i, [_vp, _sz, _vp]),
     "sd_verify_prefix": (_i, [_vp, _i, _i64, _i64, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
-                              _i, _i, _i, _i, _vp, _vp]),
+                              _i, _i, _i, _i, _vp, _vp, _vp]),
+    "sd_verify_append": (_i, [_vp, _vp]),
+    "sd_verify_append_set_interleave": (_i, [_i]),
     "sd_verify_step": (_i, [_vp, _i, _i64, _i64, _vp, _i, _i64, _i, _f, _f, _vp, _vp, _vp, _vp, _vp,
-                            _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp, _vp]),
+                            _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sd_exchange_bytes": (_sz, [_i, _i, _i]),
     "sd_exchange_alloc": (_i, [_sz, C.POINTER(_vp), _vp]),
     "sd_exchange_open": (_i, [_vp, C.POINTER(_vp)]),
@@ -48,7 +50,7 @@ SIGNATURES = {
     "sd_verify_set_variant": (_i, [_i, _i]),
     "sd_verify_set_trace": (_i, [_vp, _sz]),
     "sd_kv_append": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp,
-                          _i, _vp, _i, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+                          _i, _vp, _i, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "sd_kv_append_layer": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                                 _vp, _i, _vp, _i, _vp, _vp]),
     "sd_kv_set_variant": (_i, [_i]),
@@ -75,6 +77,24 @@ class ExchangeDesc(C.Structure):
 
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("rows_per_rank", C.c_int32), ("width", C.c_int32),
                 ("total_rows", C.c_int32), ("lag", C.c_int32), ("reserved", C.c_int32 * 2), ("peer", C.c_void_p * MAX_PEERS)]
+
+
+class StepArgs(C.Structure):
+    """struct sd_step_args (include/sd_verify.h)."""
+
+    _fields_ = [
+        ("logits", C.c_void_p), ("logit_dtype", C.c_int32), ("id_dtype", C.c_int32),
+        ("stride_b", C.c_int64), ("stride_r", C.c_int64), ("id_stride_b", C.c_int64),
+        ("draft_ids", C.c_void_p), ("accept_len", C.c_void_p), ("accepted_mask", C.c_void_p), ("target_ids", C.c_void_p),
+        ("bonus", C.c_void_p), ("packed", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("B", C.c_int32), ("rows", C.c_int32), ("K", C.c_int32), ("V", C.c_int32),
+        ("layers", C.c_void_p), ("n_layers", C.c_int32), ("H", C.c_int32), ("zero_rejected", C.c_int32),
+        ("exchange_push_in_append", C.c_int32),
+        ("row_bytes", C.c_int64), ("capacity", C.c_int64), ("arena_stride_b", C.c_int64), ("arena_stride_h", C.c_int64),
+        ("new_stride_b", C.c_int64), ("new_stride_h", C.c_int64), ("new_stride_r", C.c_int64), ("max_seq_len_host", C.c_int64),
+        ("seq_lens", C.c_void_p), ("overflow_flag", C.c_void_p), ("ticket", C.c_void_p), ("seq_ready", C.c_void_p),
+        ("exchange", C.c_void_p), ("exchange_out", C.c_void_p),
+    ]
 
 
 class SdError(RuntimeError):

@@ -129,6 +129,7 @@ def verify_launch(
     row_sumexp: Optional[torch.Tensor] = None,
     stats: bool = False,
     exchange: Optional[int] = None,
+    seq_ready: Optional[torch.Tensor] = None,
 ) -> None:
     """Enqueue one fused-verify launch into caller-owned buffers (no allocation when a workspace is
     passed).  This is the call the graph-captured step uses.  ``exchange`` = device pointer of an
@@ -150,12 +151,12 @@ def verify_launch(
                 *common, mode, float(threshold), float(inv_temperature),
                 accept_len.data_ptr(), _ptr(accepted_mask), _ptr(target_ids), _ptr(bonus), _ptr(packed),
                 _ptr(token_prob), _ptr(row_max), _ptr(row_sumexp),
-                workspace.data_ptr(), workspace.numel(), B, rows, K, V, _stream_ptr(dev), exchange,
+                workspace.data_ptr(), workspace.numel(), B, rows, K, V, _stream_ptr(dev), exchange, _ptr(seq_ready),
             )
         else:
             rc = lib.sd_verify_prefix(
                 *common, accept_len.data_ptr(), _ptr(accepted_mask), _ptr(target_ids), _ptr(bonus), _ptr(packed),
-                workspace.data_ptr(), workspace.numel(), B, rows, K, V, _stream_ptr(dev), exchange,
+                workspace.data_ptr(), workspace.numel(), B, rows, K, V, _stream_ptr(dev), exchange, _ptr(seq_ready),
             )
     lib.check(rc, "sd_verify")
 
@@ -454,6 +455,7 @@ def kv_arena_append_launch(
     exchange: Optional[int] = None,
     exchange_out: Optional[torch.Tensor] = None,
     exchange_packed: Optional[torch.Tensor] = None,
+    seq_ready: Optional[torch.Tensor] = None,
 ) -> None:
     """All-layer arena append (sd_kv_append).  ``layer_table`` is a device int64 [n_layers, 4] tensor
     of (arena_k, arena_v, new_k, new_v) pointers == sd_kv_layer[n_layers]."""
@@ -464,9 +466,68 @@ def kv_arena_append_launch(
             layer_table.data_ptr(), n_layers, B, H, R, row_bytes, capacity, arena_strides[0], arena_strides[1],
             new_strides[0], new_strides[1], new_strides[2], _ptr(seq_lens), _ptr(seq_lens_out), _ptr(n_keep),
             keep_bias, _ptr(accepted_mask), int(zero_rejected), max_seq_len_host, _ptr(overflow_flag),
-            ticket.data_ptr(), int(rows_ready_early), _stream_ptr(dev), exchange, _ptr(exchange_out), _ptr(exchange_packed),
+            ticket.data_ptr(), int(rows_ready_early), _stream_ptr(dev), exchange, _ptr(exchange_out), _ptr(exchange_packed), _ptr(seq_ready),
         )
     lib.check(rc, "sd_kv_append")
+
+
+# ------------------------------------------------------------------------------------------ fused step
+def fused_step_available(arena) -> bool:
+    """sd_verify_append needs the default bulk-chunk verify variant and 16-byte aligned, unmasked KV rows."""
+    return (_verify_variant_state["variant"] == DEFAULT_VERIFY_VARIANT and arena.row_bytes % 16 == 0
+            and _kv_variant_state["variant"] in (0, 3))
+
+
+def verify_append_launch(
+    logits: torch.Tensor,
+    draft_ids: torch.Tensor,
+    accept_len: torch.Tensor,
+    accepted_mask: Optional[torch.Tensor],
+    target_ids: Optional[torch.Tensor],
+    bonus: Optional[torch.Tensor],
+    packed: Optional[torch.Tensor],
+    workspace: torch.Tensor,
+    seq_ready: torch.Tensor,
+    arena,
+    zero_rejected: bool = True,
+    check_capacity: bool = False,
+    exchange=None,
+    exchange_push_in_append: bool = True,
+) -> None:
+    """The whole greedy verify step in ONE launch (sd_verify_append): fused verify over ``logits``
+    [B,K+1,V] + kv_append of ``arena``'s staged rows for every layer (accept_len + 1 rows kept).  ``arena`` is a
+    specdec.cache.kv_arena.KVArena; ``exchange`` a scheduler.batch_shard.PeerExchange (its records are pushed by
+    the append part when ``exchange_push_in_append`` else by the verify finalizers, and gathered by the append
+    part into ``exchange.out``)."""
+    import ctypes as C
+
+    B, rows, V = logits.shape
+    K = draft_ids.shape[1]
+    es = arena.k.element_size()
+    a = _capi.StepArgs()
+    a.logits, a.logit_dtype, a.id_dtype = logits.data_ptr(), _DTYPE[logits.dtype], _ID_DTYPE[draft_ids.dtype]
+    a.stride_b, a.stride_r, a.id_stride_b = logits.stride(0), logits.stride(1), draft_ids.stride(0)
+    a.draft_ids, a.accept_len = draft_ids.data_ptr(), accept_len.data_ptr()
+    a.accepted_mask, a.target_ids, a.bonus, a.packed = _ptr(accepted_mask), _ptr(target_ids), _ptr(bonus), _ptr(packed)
+    a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel()
+    a.B, a.rows, a.K, a.V = B, rows, K, V
+    a.layers, a.n_layers, a.H = arena.layer_table.data_ptr(), arena.n_layers, arena.n_kv_heads
+    a.zero_rejected, a.exchange_push_in_append = int(zero_rejected), int(exchange_push_in_append and exchange is not None)
+    a.row_bytes, a.capacity = arena.row_bytes, arena.capacity
+    a.arena_stride_b, a.arena_stride_h = arena.k.stride(1) * es, arena.k.stride(2) * es
+    a.new_stride_b, a.new_stride_h, a.new_stride_r = (arena.new_k.stride(1) * es, arena.new_k.stride(2) * es,
+                                                      arena.new_k.stride(3) * es)
+    a.max_seq_len_host = arena._max_len_host if check_capacity else -1
+    a.seq_lens, a.overflow_flag, a.ticket = arena.seq_lens.data_ptr(), arena.overflow.data_ptr(), arena._ticket.data_ptr()
+    a.seq_ready = seq_ready.data_ptr()
+    a.exchange = exchange.desc_ptr if exchange is not None else None
+    a.exchange_out = exchange.out.data_ptr() if exchange is not None else None
+    lib = _capi.lib()
+    dev = logits.device
+    with torch.cuda.device(dev):
+        rc = lib.sd_verify_append(C.byref(a), _stream_ptr(dev))
+    lib.check(rc, "sd_verify_append")
+    arena._max_len_host = min(arena.capacity, arena._max_len_host + rows)
 
 
 # ------------------------------------------------------------------------------------------ attention
@@ -576,7 +637,12 @@ def set_verify_tuning(threads: int = 0, vectors_per_thread: int = 0) -> None:
 DEFAULT_VERIFY_VARIANT = 3  # bulk-chunk kernel (csrc/sd_verify.cu)
 
 
+_verify_variant_state = {"variant": DEFAULT_VERIFY_VARIANT}
+_kv_variant_state = {"variant": 0}
+
+
 def set_verify_variant(variant: int = DEFAULT_VERIFY_VARIANT, ctas_per_sm: int = 0) -> None:
+    _verify_variant_state["variant"] = variant
     _capi.lib().check(_capi.lib().sd_verify_set_variant(variant, ctas_per_sm), "sd_verify_set_variant")
 
 
@@ -589,4 +655,5 @@ def set_pdl(enabled: bool = True) -> None:
 
 
 def set_kv_variant(variant: int = 0) -> None:
+    _kv_variant_state["variant"] = variant & 15
     _capi.lib().check(_capi.lib().sd_kv_set_variant(variant), "sd_kv_set_variant")

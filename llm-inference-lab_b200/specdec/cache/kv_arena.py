@@ -95,6 +95,7 @@ class KVArena:
         rows_ready_early: bool = False,
         exchange=None,
         exchange_packed: Optional[torch.Tensor] = None,
+        seq_ready: Optional[torch.Tensor] = None,
     ) -> None:
         """Append the staged rows of every layer.  ``n_keep`` [B] int32 (device) + ``keep_bias`` rows
         of each sequence are kept (None = all ``rows``); lengths advance on device.
@@ -104,7 +105,9 @@ class KVArena:
         ``exchange``: a scheduler.batch_shard.PeerExchange whose records of this step are confirmed and
         gathered (into ``exchange.out``) by the last CTA of this launch -- replaces ``exchange.wait()``.
         ``exchange_packed``: this rank's packed [B, K+2] records; when given, the first CTA of this launch
-        pushes them to the peers (then the verify launch must NOT carry the exchange)."""
+        pushes them to the peers (then the verify launch must NOT carry the exchange).
+        ``seq_ready``: the [B] int32 flag array that the verify launch just before received: the append then
+        starts per sequence as soon as that sequence is verified (overlap with the verify tail)."""
         R = self.max_new_rows if rows is None else rows
         es = self.k.element_size()
         cuda_ops.kv_arena_append_launch(
@@ -114,7 +117,7 @@ class KVArena:
             self.seq_lens, self.seq_lens, n_keep, keep_bias, accepted_mask, zero_rejected,
             self._max_len_host if check_capacity else -1, self.overflow, self._ticket, rows_ready_early,
             exchange.desc_ptr if exchange is not None else None, exchange.out if exchange is not None else None,
-            exchange_packed,
+            exchange_packed, seq_ready,
         )
         self._max_len_host = min(self.capacity, self._max_len_host + R)
 

@@ -44,6 +44,13 @@ class VerifyStep:
         self.arena = arena
         self.mode, self.threshold, self.temperature = mode, threshold, temperature
         self.rows_ready_early = False
+        # per-sequence completion flags: verify raises flag b when sequence b is final, the append that follows
+        # starts on b right away (overlaps the verify tail) and re-zeroes the flags.  Only with an arena.
+        self.seq_ready = torch.zeros(batch, dtype=torch.int32, device=self.device)
+        self.overlap_append = True
+        self.raise_flags: Optional[bool] = None  # None = whenever this object also issues the append
+        # greedy verify + append in ONE launch (sd_verify_append) when this object owns the arena
+        self.fused_launch = True
         # scheduler.batch_shard.PeerExchange: the records also go to every peer GPU.  They are confirmed and
         # gathered by the append launch when there is an arena, else by a wait kernel; set
         # ``exchange_wait = False`` when the caller issues that step itself (bench.py appends separately).
@@ -70,18 +77,33 @@ class VerifyStep:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 1 + (1 if arena is not None else 0) + (1 if bonus_sampling else 0)
 
+    def _raise_flags(self) -> bool:
+        """The flags must be consumed (and re-zeroed) by an append launch right after the verify launch; a
+        caller that appends itself (bench.py) sets ``raise_flags = True`` and passes ``seq_ready`` along."""
+        if self.raise_flags is not None:
+            return self.raise_flags
+        return self.arena is not None and self.overlap_append
+
     # -- eager ------------------------------------------------------------------------------------
     def run(self, logits: Optional[torch.Tensor] = None, draft_ids: Optional[torch.Tensor] = None) -> None:
         """Enqueue verify (+ append) on the current stream.  ``logits``/``draft_ids`` default to the
         static buffers; passing other tensors verifies them in place (no copy)."""
         lg = self.logits if logits is None else logits
         ids = self.draft_ids if draft_ids is None else draft_ids
+        if (self.fused_launch and self.arena is not None and self.mode == "greedy" and self.overlap_append
+                and self.bonus_sampling is None and cuda_ops.fused_step_available(self.arena)):
+            cuda_ops.verify_append_launch(
+                lg, ids, self.accept_len, self.accepted_mask, self.target_ids, self.bonus, self.packed, self.workspace,
+                self.seq_ready, self.arena, zero_rejected=True, check_capacity=False,
+                exchange=self.exchange if self.exchange_wait else None)
+            return
         cuda_ops.verify_launch(
             lg, ids, self.accept_len, self.accepted_mask, self.target_ids, self.bonus, self.packed, self.workspace,
             mode=cuda_ops.ACCEPT_MODES[self.mode], threshold=self.threshold, inv_temperature=1.0 / self.temperature,
             token_prob=self.token_prob, row_max=self.row_max, row_sumexp=self.row_sumexp,
             stats=self.mode != "greedy",
             exchange=self.exchange.desc_ptr if self.exchange is not None else None,
+            seq_ready=self.seq_ready if self._raise_flags() else None,
         )
         if self.bonus_sampling is not None:
             cuda_ops.sample_bonus_cuda(lg, row_index=self.accept_len, uniform=self.uniform, out=self.bonus,
@@ -94,7 +116,8 @@ class VerifyStep:
             # hold the registers until the very end -- and it reads the rejected rows too)
             self.arena.append(self.accept_len, keep_bias=1, zero_rejected=True, check_capacity=False,
                               rows_ready_early=self.rows_ready_early,
-                              exchange=self.exchange if self.exchange_wait else None)
+                              exchange=self.exchange if self.exchange_wait else None,
+                              seq_ready=self.seq_ready if self._raise_flags() else None)
         elif self.exchange is not None and self.exchange_wait:
             self.exchange.wait()
 

@@ -36,17 +36,17 @@ def test_argument_errors_are_reported_without_a_gpu():
     lib = _capi.lib()
     # rows must be K or K+1 -> SD_ERR_SHAPE, detected before any CUDA call
     rc = lib.sd_verify_prefix(1, _capi.DTYPE_BF16, 0, 0, 1, _capi.ID_I64, 0, 1, None, None, None, None, 1, 1 << 30,
-                              2, 7, 4, 100, None, None)
+                              2, 7, 4, 100, None, None, None)
     assert rc == -2
     rc = lib.sd_verify_prefix(None, _capi.DTYPE_BF16, 0, 0, 1, _capi.ID_I64, 0, 1, None, None, None, None, 1, 1 << 30,
-                              2, 5, 4, 100, None, None)
+                              2, 5, 4, 100, None, None, None)
     assert rc == -1
     assert lib.sd_verify_set_tuning(100, 4) == -1  # threads must be a multiple of 32
     assert lib.sd_verify_set_tuning(256, 17) == -1
     assert lib.sd_verify_set_tuning(0, 0) == 0
     assert lib.sd_kv_set_variant(7) == -1
     # capacity check on host-known sizes
-    rc = lib.sd_kv_append(1, 1, 1, 1, 5, 256, 8, 0, 0, 0, 0, 0, None, None, None, 0, None, 1, 4, None, 1, 0, None, None, None, None)
+    rc = lib.sd_kv_append(1, 1, 1, 1, 5, 256, 8, 0, 0, 0, 0, 0, None, None, None, 0, None, 1, 4, None, 1, 0, None, None, None, None, None)
     assert rc == -6
 
 

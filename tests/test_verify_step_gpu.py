@@ -275,3 +275,41 @@ def test_peer_exchange_pushed_and_gathered_by_the_append_launch():
     finally:
         for x in xs:
             x.close()
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+@pytest.mark.parametrize("overlap", [True, False])
+def test_append_overlapping_the_verify_tail(use_graph, overlap):
+    """Per-sequence flags (seq_ready): the append starts on a sequence as soon as that sequence is verified.
+    Same results as the serialised form, over many steps (flags re-armed every step), Llama-like row size."""
+    B, K, V, layers, H, D, L, cap = 48, 4, 32000, 4, 8, 128, 7, 96
+    dev = torch.device("cuda")
+    arena = KVArena(layers, B, H, D, cap, K + 1, torch.bfloat16, dev)
+    g = torch.Generator().manual_seed(2)
+    arena.k[:, :, :, :L] = torch.randn(layers, B, H, L, D, generator=g).to(torch.bfloat16).cuda()
+    arena.v[:, :, :, :L] = torch.randn(layers, B, H, L, D, generator=g).to(torch.bfloat16).cuda()
+    arena.set_lengths([L] * B)
+    step = VerifyStep(B, K, V, arena=arena, device=dev)
+    step.overlap_append = overlap
+    exp_k, exp_v = to_np(arena.k).copy(), to_np(arena.v).copy()
+    lens = np.full(B, L, np.int32)
+    if use_graph:
+        step.capture()
+        arena.set_lengths([L] * B)
+        arena.k.copy_(torch.from_numpy(exp_k.view(np.int16)).view(torch.bfloat16))
+        arena.v.copy_(torch.from_numpy(exp_v.view(np.int16)).view(torch.bfloat16))
+    for it in range(6):
+        logits, ids = make_verify_inputs(B, K + 1, K, V, "bf16", p_match=0.75, seed=900 + it, device="cuda")
+        step.logits.copy_(logits)
+        step.draft_ids.copy_(ids)
+        arena.new_k.copy_(torch.randn(arena.new_k.shape, generator=g).to(torch.bfloat16))
+        arena.new_v.copy_(torch.randn(arena.new_v.shape, generator=g).to(torch.bfloat16))
+        torch.cuda.synchronize()
+        step.replay() if use_graph else step.run()
+        torch.cuda.synchronize()
+        acc, mask, tgt, bonus, lens = _oracle_step(exp_k, exp_v, lens, logits, ids, to_np(arena.new_k), to_np(arena.new_v))
+        np.testing.assert_array_equal(step.accept_len.cpu().numpy(), acc)
+        np.testing.assert_array_equal(arena.seq_lens.cpu().numpy(), lens)
+        np.testing.assert_array_equal(to_np(arena.k), exp_k)
+        np.testing.assert_array_equal(to_np(arena.v), exp_v)
+        assert int(step.seq_ready.sum()) == 0  # re-armed
