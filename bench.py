@@ -501,7 +501,8 @@ def run_ours(args):
             "pipelined_exchange": ({"lag_steps": 1, "ms_per_step": lag1_ms, "value": tokens_per_step_all / (lag1_ms * 1e-3),
                                     "note": "same step, but each append gathers the PREVIOUS step's records: ranks are not in lockstep; "
                                             "every rank still has its own shard's records immediately"} if lag1_ms > 0 else None),
-            "roofline": {"bound": "hbm", "kernel": "verify_bulk_kernel<bf16> (one cp.async.bulk per CTA chunk)", "achieved": v_gbs, "peak": peak, "unit": "GB/s",
+            "roofline": None,
+            "roofline_verify": {"bound": "hbm", "kernel": "verify_bulk_kernel<bf16> (one cp.async.bulk per CTA chunk), timed alone", "achieved": v_gbs, "peak": peak, "unit": "GB/s",
                          "frac": v_gbs / peak, "frac_of_8TBs_nominal": v_gbs / 8000.0, "traffic": traffic.get("verify_bulk_kernel"),
                          "algorithmic_bytes": verify_bytes, "us_per_launch": verify_ms * 1e3, "peak_source": peak_src},
             "roofline_kv": {"bound": "hbm", "kernel": "kv_append_col_kernel<5> (all 28 layers, one launch)", "achieved": kv_gbs, "peak": peak, "unit": "GB/s",
@@ -515,6 +516,18 @@ def run_ours(args):
             "step_hbm_frac": (verify_bytes + kv_bytes) / (step_ms * 1e-3) / 1e9 / peak,
             "clocks": clocks, "wall_s_timed_region": t_wall,
         }
+        if args.no_fuse:
+            line["roofline"] = dict(line["roofline_verify"], kernel="verify_bulk_kernel<bf16> (dominant kernel of the two-launch step)")
+        else:
+            # the timed region launches ONE kernel per step: the fused verify + append kernel is the dominant kernel
+            step_bytes = verify_bytes + kv_bytes
+            step_gbs = step_bytes / (step_ms * 1e-3) / 1e9
+            line["roofline"] = {"bound": "hbm", "kernel": "verify_append_kernel<bf16,5> (the whole step in one launch: fused verify + kv_append of 28 layers)",
+                                "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
+                                "frac_of_8TBs_nominal": step_gbs / 8000.0, "traffic": traffic.get("verify_append_kernel"),
+                                "algorithmic_bytes": step_bytes, "us_per_launch": step_ms * 1e3, "peak_source": peak_src,
+                                "note": "algorithmic bytes = logits read once (82.08 MB) + accepted KV rows read + offered slots written "
+                                        "(60.2 MB at 3.2 rows kept); duration = CUDA-event time of the timed region / launches"}
         if e2e:
             line["e2e"] = {"value": e2e_tokens_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
                            "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,

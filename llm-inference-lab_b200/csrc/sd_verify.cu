@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(256) verify_bulk_kernel(const VerifyParams p) 
 // resident only when every verify CTA has started; they wait on flags, verify CTAs wait on nothing that
 // an append CTA produces -> no deadlock.  One launch overhead, one ramp and one tail per step instead of two.
 template <typename T, int RB>
-__global__ void __launch_bounds__(256) verify_append_kernel(const VerifyParams vp, const KvParams kp, const int n_verify,
+__global__ void __launch_bounds__(256, 4) verify_append_kernel(const VerifyParams vp, const KvParams kp, const int n_verify,
                                                             const int kv_gx, const int interleave_group) {
     extern __shared__ __align__(128) unsigned char stage[];
     __shared__ __align__(8) uint64_t bar;
@@ -1108,7 +1108,10 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
         if (variant != 3 || stats) return SD_ERR_UNSUPPORTED;
         const size_t smem = (size_t)p.units_per_chunk * threads * 16;
         const unsigned total = grid + fused_gx * (unsigned)fused_kv->n_layers;
-        return to_status(launch_fused(p, *fused_kv, logit_dtype, fused_rb, total, (int)grid, (int)fused_gx, threads, smem, st));
+        // RB <= 3 rows of K and V in flight per append thread keeps the fused kernel at <= 64 registers, i.e. four
+        // resident CTAs per SM for the verify part (at RB = 5 it needs 80 registers: three CTAs, 35 % occupancy)
+        const int rb = fused_rb > 3 ? 3 : fused_rb;
+        return to_status(launch_fused(p, *fused_kv, logit_dtype, rb, total, (int)grid, (int)fused_gx, threads, smem, st));
     }
     if (variant == 3) {
         const size_t smem = (size_t)p.units_per_chunk * threads * 16;
