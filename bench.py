@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--tuning", default="", help="threads,vectors_per_thread for the verify kernel (sweeps)")
     ap.add_argument("--kv-variant", type=int, default=0)
     ap.add_argument("--batch", type=int, default=CFG["B"], help="sequences per GPU")
+    ap.add_argument("--force-fuse", action="store_true", help="N>1: keep the fused verify+append launch")
     ap.add_argument("--no-fuse", action="store_true", help="two launches per step (verify, kv_append) instead of sd_verify_append")
     ap.add_argument("--interleave", action="store_true", help="fused launch: append CTAs of a sequence group right after its verify CTAs")
     ap.add_argument("--no-overlap", action="store_true",
@@ -245,6 +246,15 @@ def run_ours(args):
     if args.interleave:
         cuda_ops._capi.lib().sd_verify_append_set_interleave(1)
 
+    # Launch structure per step (measured): one GPU -> the fused verify+append launch;
+    # several GPUs -> two launches with PDL, the append pushing this rank's records to the peers at its START
+    # (the NVLink round trip hides behind the copy) and gathering at the end.  With the per-sequence flags /
+    # the fused launch the push would only start once the last sequence is verified (N=8: 38.9 vs 37.0 us).
+    if world > 1 and not args.force_fuse:
+        args.no_fuse = True
+        args.no_overlap = True
+    if args.exchange == "peer":
+        args.no_fuse = True
     B, K, V, NB = args.batch, CFG["K"], CFG["V"], CFG["nbuf"]
     R = K + 1
     total_steps = args.steps + args.warmup

@@ -281,7 +281,8 @@ int sd_kv_append_layer(void* arena_k, void* arena_v, const void* new_k, const vo
  * but the append CTAs are part of the verify grid (dispatched after the verify CTAs, waiting on the
  * per-sequence flags), so a step pays one launch, one ramp and one tail instead of two.
  * Requirements: greedy acceptance, unmasked 16-byte aligned KV rows (the column kernel), the
- * bulk-chunk verify variant (the default).  Otherwise SD_ERR_UNSUPPORTED: issue the two launches.
+ * bulk-chunk verify variant (the default); with `exchange`, exchange_push_in_append must be set (the
+ * records are pushed and gathered by the append part).  Otherwise SD_ERR_UNSUPPORTED: issue the two launches.
  */
 typedef struct sd_step_args {
     /* fused verify: see sd_verify_prefix */

@@ -1210,6 +1210,11 @@ int sd_verify_append(const sd_step_args* a, void* stream) {
     if (!a) return SD_ERR_INVALID_ARG;
     if (a->rows != a->K + 1) return SD_ERR_SHAPE;  // the append keeps accept_len + 1 of the K + 1 offered rows
     if (!a->seq_ready || !a->accept_len) return SD_ERR_INVALID_ARG;
+    // With an exchange, the records must be pushed by the append part: the combination "verify finalizers
+    // push + append part gathers" inside ONE grid hung at N = 8 (round 1, gpurun_out/bench19.log) and is
+    // refused until it is understood; use the two-launch form for it.
+    if (a->exchange && !a->exchange_push_in_append) return SD_ERR_UNSUPPORTED;
+    if (a->exchange && !a->packed) return SD_ERR_INVALID_ARG;
     if (a->B <= 0) return SD_OK;
     KvParams kp;
     unsigned gx = 0;
