@@ -85,21 +85,17 @@ def get_graph_capture() -> GraphCapture:
     return _graph_capture
 
 
-def can_capture() -> bool:
-    return get_graph_capture().can_capture()
+def _on_global_instance(method: str):
+    """Module-level helper forwarding to the process-wide instance (reference: graph_capture.py:124-146)."""
+
+    def call(*args: Any, **kwargs: Any) -> Any:
+        return getattr(get_graph_capture(), method)(*args, **kwargs)
+
+    call.__name__ = method
+    call.__doc__ = f"``get_graph_capture().{method}(...)``"
+    return call
 
 
-def capture_once(fn: Callable, sample_inputs: Any = None) -> bool:
-    return get_graph_capture().capture_once(fn, sample_inputs)
-
-
-def replay() -> Any:
-    return get_graph_capture().replay()
-
-
-def is_ready() -> bool:
-    return get_graph_capture().is_ready()
-
-
-def reset() -> None:
-    get_graph_capture().reset()
+can_capture, capture_once, replay, is_ready, reset = (
+    _on_global_instance(m) for m in ("can_capture", "capture_once", "replay", "is_ready", "reset")
+)
