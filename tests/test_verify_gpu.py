@@ -255,3 +255,19 @@ def test_torch_custom_op_entry_point():
     e_acc, e_mask = O.verify_prefix(to_np(logits), to_np(ids), "bf16")
     np.testing.assert_array_equal(acc.cpu().numpy(), e_acc)
     np.testing.assert_array_equal(mask.cpu().numpy(), e_mask)
+
+
+def test_sharded_batch_shape_b256_k8():
+    """BASELINE configs[4] per-GPU shard at G=2 (B=256) with the largest K of configs[1] (K=8), V=128256 bf16
+    (591 MB of logits): argmax tokens against torch.argmax on device, accept lengths / bonus through the
+    leading-run property, a bounded sample against the full oracle."""
+    B, K, V = 256, 8, 128256
+    logits, ids = make_verify_inputs(B, K + 1, K, V, "bf16", p_match=0.85, seed=4321, device="cuda")
+    acc, mask, tgt, bonus, packed = cuda_ops.verify_prefix_bonus_cuda(logits, ids)
+    e = torch.argmax(logits, dim=-1)
+    assert torch.equal(tgt.long(), e)
+    e_acc = torch.cumprod((e[:, :K] == ids).int(), dim=1).sum(1)
+    assert torch.equal(acc.long(), e_acc) and int(acc.max()) == K
+    assert torch.equal(bonus.long(), e[torch.arange(B, device="cuda"), acc.long()])
+    assert torch.equal(mask.sum(1).long(), acc.long())
+    _check_bonus(logits[250:], ids[250:])
