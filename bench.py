@@ -542,7 +542,7 @@ def run_ours(args):
             line["e2e"] = {"value": e2e_tokens_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
                            "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
                            "api": "VerifyStep static buffers <- pinned host tensors; packed [B,K+2] record -> host"}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported baseline: rank 0 at N=1 only
             cores = os.cpu_count() or 1
             tv, tk, reps = cpu_port_step_time(B, K, V, 2, CFG["Hkv"], CFG["D"], CFG["L"], 4, 3, cores)
             t_cpu = tv + tk * CFG["layers"]
