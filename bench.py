@@ -188,14 +188,15 @@ def run_reference_arm(args):
     t_step = tv + tk * CFG["layers"]
     mean_tokens = B * (1 + expected_accept(CFG["p_match"], K))
     value = mean_tokens / t_step
-    sample = (f"median of {reps} steps: verify_prefix+bonus port on full [B={B},K+1={K + 1},V={V}] bf16 logits; "
+    sample = (f"one host processes the job: median of {reps} steps over a {B}-sequence slice of the global batch (CPU tokens/s does not "
+              f"depend on the batch size: both legs are linear in B): verify_prefix+bonus port on [B={B},K+1={K + 1},V={V}] bf16 logits; "
               f"kv_append_ref (torch.cat, L={CFG['L']}, {keep_rows} rows) timed on {layers_sample} of {CFG['layers']} layers "
               f"and scaled to {CFG['layers']}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "verify_ms": tv * 1e3, "kv_append_ms_per_layer": tk * 1e3},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
