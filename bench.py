@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=CFG["B"], help="sequences per GPU")
     ap.add_argument("--force-fuse", action="store_true", help="N>1: keep the fused verify+append launch")
     ap.add_argument("--no-fuse", action="store_true", help="two launches per step (verify, kv_append) instead of sd_verify_append")
+    ap.add_argument("--copy-all", action="store_true", help="fused launch, copy-all mode (append CTAs copy all K+1 rows up front)")
     ap.add_argument("--interleave", action="store_true", help="fused launch: append CTAs of a sequence group right after its verify CTAs")
     ap.add_argument("--no-overlap", action="store_true",
                     help="kv_append waits for the whole verify grid (PDL) instead of per-sequence flags")
@@ -246,6 +247,8 @@ def run_ours(args):
         cuda_ops.set_kv_variant(args.kv_variant)
     if args.interleave:
         cuda_ops._capi.lib().sd_verify_append_set_interleave(1)
+    if args.copy_all:
+        cuda_ops.set_fused_copy_all(True)
 
     # Launch structure per step (measured): one GPU -> the fused verify+append launch;
     # several GPUs -> two launches with PDL, the append pushing this rank's records to the peers at its START

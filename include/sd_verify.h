@@ -310,9 +310,17 @@ typedef struct sd_step_args {
     /* multi-GPU exchange (nullable) */
     const sd_exchange* exchange;
     int32_t* exchange_out;
+    /* copy-all mode (sd_verify_append_set_copy_all): 2 * ceil(B * H * row_bytes / 16 / 256) uint32, zero before
+     * the first launch (the kernel re-zeroes them); nullable -> the flag-wait mode is used */
+    void* group_counters;
 } sd_step_args;
 
 int sd_verify_append(const sd_step_args* args, void* stream);
+/* Copy-all mode of sd_verify_append (off by default): the append CTAs copy ALL K+1 offered rows without waiting
+ * for anything and sit in front of their sequences' verify CTAs in block order; each sequence's verify finalizer
+ * then zeroes the rejected slots and advances the length.  Same results; +1 row-set of traffic for the rejected
+ * rows (written twice), no serialised append phase.  Single-GPU only (SD_ERR_UNSUPPORTED with an exchange). */
+int sd_verify_append_set_copy_all(int enabled);
 /* Evidence runs: 0 (default) = all append CTAs after all verify CTAs; 1 = the append CTAs of a group of
  * sequences directly follow that group's verify CTAs in block order.  Measured on B200 the interleaved
  * order is slower (43 vs 34 us per step): the waiting append CTAs hold registers the verify CTAs need. */

@@ -196,6 +196,126 @@ SD_DEVINL void kv_col_body(const KvParams& p, const int cta_x, const int layer) 
 }
 
 
+// ---- "copy-all" append for the fused step (mode 2 of sd_verify_append) -------------------------------
+// The append CTAs copy ALL R offered rows of their sequences and therefore depend on nothing the verify
+// part produces: they never wait, so they can sit in front of their group's verify CTAs in block order
+// and stream concurrently.  What does depend on accept_len -- zeroing the rejected slots and advancing
+// the length -- is done by the verify finalizer of the sequence, after the copy CTAs of its group have
+// signalled completion (group counter).
+struct FusedAppend {
+    int enabled;
+    const sd_kv_layer* layers;
+    int n_layers, H, R, spc;  // spc = sequences per group (per append x-slot)
+    int64_t row_bytes, capacity, arena_stride_b, arena_stride_h;
+    int32_t* seq_lens;
+    int32_t* overflow;
+    unsigned* group_cnt;      // [2 * groups]: {copy CTAs done, finalizers done}; all zero between launches
+    int zero_rejected;
+};
+
+template <int RB>
+SD_DEVINL void kv_copy_all_body(const KvParams& p, const int cta_x, const int layer, unsigned* group_cnt) {
+    const int vpr = (int)(p.row_bytes >> 4);
+    const int64_t slots = (int64_t)p.B * p.H * vpr;
+    const int64_t slot = (int64_t)cta_x * blockDim.x + threadIdx.x;
+    if (slot < slots) {
+        const int v = (int)(slot % vpr);
+        const int64_t t = slot / vpr;
+        const int h = (int)(t % p.H);
+        const int b = (int)(t / p.H);
+        const sd_kv_layer L = p.layers[layer];
+        const int len = p.seq_lens ? p.seq_lens[b] : 0;  // the finalizer advances it only after this CTA has signalled
+        int room = (int)(p.capacity - len);
+        room = room < 0 ? 0 : (room > p.R ? p.R : room);
+        const char* sk = reinterpret_cast<const char*>(L.new_k) + (int64_t)b * p.new_stride_b + (int64_t)h * p.new_stride_h + ((int64_t)v << 4);
+        const char* sv = reinterpret_cast<const char*>(L.new_v) + (int64_t)b * p.new_stride_b + (int64_t)h * p.new_stride_h + ((int64_t)v << 4);
+        const int64_t doff = (int64_t)b * p.arena_stride_b + (int64_t)h * p.arena_stride_h + (int64_t)len * p.row_bytes + ((int64_t)v << 4);
+        char* dk = reinterpret_cast<char*>(L.arena_k) + doff;
+        char* dv = reinterpret_cast<char*>(L.arena_v) + doff;
+        for (int j0 = 0; j0 < room; j0 += RB) {
+            uint4 kx[RB], vx[RB];
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {
+                const int j = j0 + u;
+                if (j < room) {
+                    kx[u] = ldg_stream_v4(sk + (int64_t)j * p.new_stride_r);
+                    vx[u] = ldg_stream_v4(sv + (int64_t)j * p.new_stride_r);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {
+                const int j = j0 + u;
+                if (j < room) {
+                    *reinterpret_cast<uint4*>(dk + (int64_t)j * p.row_bytes) = kx[u];
+                    *reinterpret_cast<uint4*>(dv + (int64_t)j * p.row_bytes) = vx[u];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();  // the rows are visible before the finalizer (which may zero some of them) sees the count
+        atomicAdd(group_cnt + 2 * cta_x, 1u);
+    }
+}
+
+// The accept_len-dependent part of the append for sequence b, run by the verify finalizer CTA (all `nthreads`
+// threads): wait for the copy CTAs of b's group, zero the rejected slots, advance the length.
+SD_DEVINL void fused_append_finalize(const FusedAppend& fa, const int b, const int n_keep, const int tid, const int nthreads,
+                                     const bool named_barrier) {
+    const int g = b / fa.spc;
+    if (tid == 0) {
+        unsigned v;
+        for (;;) {
+            asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(fa.group_cnt + 2 * g) : "memory");
+            if (v >= (unsigned)fa.n_layers) break;
+            __nanosleep(64);
+        }
+        __threadfence();
+    }
+    if (named_barrier) asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+    else __syncthreads();
+    const int len = fa.seq_lens[b];
+    int room = (int)(fa.capacity - len);
+    room = room < 0 ? 0 : (room > fa.R ? fa.R : room);
+    int n = n_keep < 0 ? 0 : (n_keep > fa.R ? fa.R : n_keep);
+    if (n > room) {
+        if (fa.overflow && tid == 0) *fa.overflow = 1;
+        n = room;
+    }
+    if (fa.zero_rejected && room > n) {
+        const int vpr = (int)(fa.row_bytes >> 4);
+        const int rej = room - n;
+        const int64_t items = (int64_t)fa.n_layers * 2 * fa.H * rej * vpr;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int64_t i = tid; i < items; i += nthreads) {
+            const int v = (int)(i % vpr);
+            int64_t t = i / vpr;
+            const int j = (int)(t % rej);
+            t /= rej;
+            const int h = (int)(t % fa.H);
+            t /= fa.H;
+            const int kv = (int)(t & 1);
+            const int layer = (int)(t >> 1);
+            const sd_kv_layer L = fa.layers[layer];
+            char* dst = reinterpret_cast<char*>(kv ? L.arena_v : L.arena_k) + (int64_t)b * fa.arena_stride_b +
+                        (int64_t)h * fa.arena_stride_h + (int64_t)(len + n + j) * fa.row_bytes + ((int64_t)v << 4);
+            *reinterpret_cast<uint4*>(dst) = z;
+        }
+    }
+    if (named_barrier) asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+    else __syncthreads();
+    if (tid == 0) {
+        fa.seq_lens[b] = len + n;
+        // the last finalizer of the group re-arms its counters for the next launch
+        const unsigned done = atomicAdd(fa.group_cnt + 2 * g + 1, 1u);
+        if (done + 1u == (unsigned)fa.spc) {
+            fa.group_cnt[2 * g] = 0u;
+            fa.group_cnt[2 * g + 1] = 0u;
+        }
+    }
+}
+
 // Validates the arguments of sd_kv_append for the column kernel and fills `out`, the (x, layers) grid and the
 // load batch RB.  Returns SD_OK, an sd_status, or SD_ERR_UNSUPPORTED when the column kernel cannot serve the call.
 int kv_prepare_col(const sd_kv_layer* layers, int n_layers, int B, int H, int R, int64_t row_bytes, int64_t capacity,

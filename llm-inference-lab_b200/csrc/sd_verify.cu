@@ -75,6 +75,7 @@ struct VerifyParams {
     float inv_temperature;
     const sd_exchange* xchg;    // nullable: peer-memory result exchange (device memory)
     int32_t* seq_ready;         // nullable: flag b is raised once sequence b's outputs are final
+    FusedAppend fa;             // copy-all fused step: the finalizer zeroes the rejected KV slots and advances the length
     unsigned long long* trace;  // evidence runs: [grid][4] = {globaltimer at entry, after the scan, at exit, smid}
 };
 
@@ -507,6 +508,12 @@ SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int n
             }
         }
     }
+    if (p.fa.enabled) {
+        __shared__ int s_nacc;
+        if (tid == 0) s_nacc = p.accept_len[b];  // written by this thread a few lines above
+        cta_sync<NAMED>(nthreads);
+        fused_append_finalize(p.fa, b, s_nacc + 1, tid, nthreads, NAMED);
+    }
     if (wid == 0 && p.seq_ready) {
         // per-sequence completion flag: lets the kv_append launch that follows start on sequence b while other
         // sequences are still being verified (sd_kv_append, seq_ready)
@@ -812,6 +819,14 @@ __global__ void __launch_bounds__(256, 4) verify_append_kernel(const VerifyParam
     __syncthreads();
     pdl_wait();
     pdl_trigger();
+    if (vp.fa.enabled) {
+        // copy-all mode: group = [append CTAs of the group's sequences: one per layer, copying all R rows, waiting
+        // on nothing][the group's verify CTAs, whose finalizers zero the rejected slots and advance the lengths]
+        const int g = (int)blockIdx.x / interleave_group, r = (int)blockIdx.x - g * interleave_group;
+        if (r < kp.n_layers) kv_copy_all_body<RB>(kp, g, r, vp.fa.group_cnt);
+        else verify_bulk_body<T, false>(vp, g * (interleave_group - kp.n_layers) + (r - kp.n_layers), stage, &bar);
+        return;
+    }
     if (interleave_group > 0) {
         // Interleaved order: the append CTAs of a group of sequences come right after that group's verify CTAs,
         // so they are dispatched in the middle of the grid, wait about one CTA lifetime for their flags and
@@ -899,6 +914,7 @@ static cudaError_t launch_bulk_t(const VerifyParams& p, unsigned grid, int threa
     return launch_kernel(verify_bulk_kernel<T, STATS>, dim3(grid), dim3(threads), smem, st, p);
 }
 
+static int g_fused_copy_all = 0;    // 1 = copy-all fused step (needs a group-counter workspace, see sd_verify_append)
 static int g_fused_interleave = 0;  // evidence runs: 1 = append CTAs of a sequence group right after its verify CTAs (measured slower: 43 vs 34 us)
 
 template <typename T, int RB>
@@ -906,11 +922,12 @@ static cudaError_t launch_fused_t(const VerifyParams& p, const KvParams& kp, uns
                                   int threads, size_t smem, cudaStream_t st) {
     // interleaving needs whole sequences per append x-slot and whole groups: n_verify = kv_gx * verify_per_group
     int group = 0;
-    if (g_fused_interleave && kv_gx > 0 && n_verify % kv_gx == 0) {
+    if ((g_fused_interleave || p.fa.enabled) && kv_gx > 0 && n_verify % kv_gx == 0) {
         const long long threads_per_seq = (long long)kp.H * (kp.row_bytes / 16);
         if (threads_per_seq > 0 && 256 % threads_per_seq == 0 && ((long long)kp.B * threads_per_seq) % 256 == 0)
             group = n_verify / kv_gx + kp.n_layers;
     }
+    if (p.fa.enabled && group == 0) return cudaErrorInvalidConfiguration;  // checked by the caller; never launch half a protocol
     cudaError_t e = cudaFuncSetAttribute(verify_append_kernel<T, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return launch_kernel(verify_append_kernel<T, RB>, dim3(total), dim3(threads), smem, st, p, kp, n_verify, kv_gx, group);
@@ -974,7 +991,8 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
                       int32_t* target_ids, int32_t* bonus, int32_t* packed, float* token_prob,
                       float* row_max, float* row_sumexp, void* workspace, size_t workspace_bytes, int B,
                       int rows, int K, int V, void* stream, const sd_exchange* exchange, int32_t* seq_ready,
-                      const KvParams* fused_kv = nullptr, unsigned fused_gx = 0, int fused_rb = 0) {
+                      const KvParams* fused_kv = nullptr, unsigned fused_gx = 0, int fused_rb = 0,
+                      unsigned* fused_group_cnt = nullptr) {
     if (B < 0 || K < 0 || V <= 0 || rows <= 0) return SD_ERR_INVALID_ARG;
     if (rows != K && rows != K + 1) return SD_ERR_SHAPE;
     if (rows > 64) return SD_ERR_UNSUPPORTED;
@@ -1058,6 +1076,7 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
     p.trace = nullptr;
     p.xchg = exchange;
     p.seq_ready = seq_ready;
+    p.fa.enabled = 0;
 
     unsigned grid;
     int tma_stages = 0;
@@ -1106,6 +1125,27 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
     cudaError_t e;
     if (fused_kv) {
         if (variant != 3 || stats) return SD_ERR_UNSUPPORTED;
+        if (fused_group_cnt) {
+            // copy-all mode: whole groups only (whole sequences per append x-slot, whole x-slots per batch)
+            const long long tps = (long long)fused_kv->H * (fused_kv->row_bytes / 16);
+            const bool whole = fused_gx > 0 && grid % fused_gx == 0 && tps > 0 && 256 % tps == 0 && ((long long)B * tps) % 256 == 0;
+            if (!whole || fused_kv->xchg) return SD_ERR_UNSUPPORTED;
+            p.fa.enabled = 1;
+            p.fa.layers = fused_kv->layers;
+            p.fa.n_layers = fused_kv->n_layers;
+            p.fa.H = fused_kv->H;
+            p.fa.R = fused_kv->R;
+            p.fa.spc = (int)(256 / tps);
+            p.fa.row_bytes = fused_kv->row_bytes;
+            p.fa.capacity = fused_kv->capacity;
+            p.fa.arena_stride_b = fused_kv->arena_stride_b;
+            p.fa.arena_stride_h = fused_kv->arena_stride_h;
+            p.fa.seq_lens = fused_kv->seq_lens_out;
+            p.fa.overflow = fused_kv->overflow;
+            p.fa.group_cnt = fused_group_cnt;
+            p.fa.zero_rejected = fused_kv->zero_rejected;
+            p.seq_ready = nullptr;
+        }
         const size_t smem = (size_t)p.units_per_chunk * threads * 16;
         const unsigned total = grid + fused_gx * (unsigned)fused_kv->n_layers;
         // RB <= 3 rows of K and V in flight per append thread keeps the fused kernel at <= 64 registers, i.e. four
@@ -1200,6 +1240,11 @@ int sd_verify_prefix(const void* logits, int logit_dtype, int64_t stride_b, int6
                           nullptr, nullptr, nullptr, workspace, workspace_bytes, B, rows, K, V, stream, exchange, seq_ready);
 }
 
+int sd_verify_append_set_copy_all(int enabled) {
+    sd::g_fused_copy_all = enabled ? 1 : 0;
+    return SD_OK;
+}
+
 int sd_verify_append_set_interleave(int enabled) {
     sd::g_fused_interleave = enabled ? 1 : 0;
     return SD_OK;
@@ -1227,7 +1272,8 @@ int sd_verify_append(const sd_step_args* a, void* stream) {
     return run_verify(false, a->logits, a->logit_dtype, a->stride_b, a->stride_r, a->draft_ids, a->id_dtype, a->id_stride_b,
                       SD_ACCEPT_GREEDY, 0.f, 1.f, a->accept_len, a->accepted_mask, a->target_ids, a->bonus, a->packed, nullptr,
                       nullptr, nullptr, a->workspace, a->workspace_bytes, a->B, a->rows, a->K, a->V, stream,
-                      a->exchange_push_in_append ? nullptr : a->exchange, a->seq_ready, &kp, gx, rb);
+                      a->exchange_push_in_append ? nullptr : a->exchange, a->seq_ready, &kp, gx, rb,
+                      (g_fused_copy_all && !a->exchange) ? reinterpret_cast<unsigned*>(a->group_counters) : nullptr);
 }
 
 int sd_verify_step(const void* logits, int logit_dtype, int64_t stride_b, int64_t stride_r,

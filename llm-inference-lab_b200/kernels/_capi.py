@@ -38,6 +38,7 @@ SIGNATURES = {
                               _i, _i, _i, _i, _vp, _vp, _vp]),
     "sd_verify_append": (_i, [_vp, _vp]),
     "sd_verify_append_set_interleave": (_i, [_i]),
+    "sd_verify_append_set_copy_all": (_i, [_i]),
     "sd_verify_step": (_i, [_vp, _i, _i64, _i64, _vp, _i, _i64, _i, _f, _f, _vp, _vp, _vp, _vp, _vp,
                             _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sd_exchange_bytes": (_sz, [_i, _i, _i]),
@@ -93,7 +94,7 @@ class StepArgs(C.Structure):
         ("row_bytes", C.c_int64), ("capacity", C.c_int64), ("arena_stride_b", C.c_int64), ("arena_stride_h", C.c_int64),
         ("new_stride_b", C.c_int64), ("new_stride_h", C.c_int64), ("new_stride_r", C.c_int64), ("max_seq_len_host", C.c_int64),
         ("seq_lens", C.c_void_p), ("overflow_flag", C.c_void_p), ("ticket", C.c_void_p), ("seq_ready", C.c_void_p),
-        ("exchange", C.c_void_p), ("exchange_out", C.c_void_p),
+        ("exchange", C.c_void_p), ("exchange_out", C.c_void_p), ("group_counters", C.c_void_p),
     ]
 
 

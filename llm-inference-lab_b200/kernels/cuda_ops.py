@@ -522,6 +522,7 @@ def verify_append_launch(
     a.seq_ready = seq_ready.data_ptr()
     a.exchange = exchange.desc_ptr if exchange is not None else None
     a.exchange_out = exchange.out.data_ptr() if exchange is not None else None
+    a.group_counters = arena.group_counters().data_ptr()
     lib = _capi.lib()
     dev = logits.device
     with torch.cuda.device(dev):
@@ -648,6 +649,11 @@ def set_verify_variant(variant: int = DEFAULT_VERIFY_VARIANT, ctas_per_sm: int =
 
 def set_attention_tuning(config: int = 0) -> None:
     _capi.lib().check(_capi.lib().sd_verify_attention_set_tuning(config), "sd_verify_attention_set_tuning")
+
+
+def set_fused_copy_all(enabled: bool = True) -> None:
+    """Copy-all mode of the fused step (include/sd_verify.h: sd_verify_append_set_copy_all)."""
+    _capi.lib().check(_capi.lib().sd_verify_append_set_copy_all(int(enabled)), "sd_verify_append_set_copy_all")
 
 
 def set_pdl(enabled: bool = True) -> None:

@@ -50,6 +50,13 @@ class KVArena:
         self.layer_table = self._build_table(self.new_k, self.new_v)
         self._max_len_host = 0  # host-side upper bound of seq_lens, for the capacity check
 
+    def group_counters(self) -> torch.Tensor:
+        """Zero-initialised counters for the copy-all fused step (2 per append x-slot; the kernel re-zeroes them)."""
+        if getattr(self, "_group_counters", None) is None:
+            slots = self.batch * self.n_kv_heads * (self.row_bytes // 16)
+            self._group_counters = torch.zeros(2 * ((slots + 255) // 256) + 2, dtype=torch.int32, device=self.device)
+        return self._group_counters
+
     # -- layout helpers -------------------------------------------------------------------------
     def _build_table(self, new_k: torch.Tensor, new_v: torch.Tensor) -> torch.Tensor:
         rows = [

@@ -278,7 +278,7 @@ def test_peer_exchange_pushed_and_gathered_by_the_append_launch():
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
-@pytest.mark.parametrize("overlap", [True, False])
+@pytest.mark.parametrize("overlap", [True, False, "copy_all"])
 def test_append_overlapping_the_verify_tail(use_graph, overlap):
     """Per-sequence flags (seq_ready): the append starts on a sequence as soon as that sequence is verified.
     Same results as the serialised form, over many steps (flags re-armed every step), Llama-like row size."""
@@ -290,7 +290,11 @@ def test_append_overlapping_the_verify_tail(use_graph, overlap):
     arena.v[:, :, :, :L] = torch.randn(layers, B, H, L, D, generator=g).to(torch.bfloat16).cuda()
     arena.set_lengths([L] * B)
     step = VerifyStep(B, K, V, arena=arena, device=dev)
-    step.overlap_append = overlap
+    copy_all = overlap == "copy_all"  # fused step whose append CTAs copy all rows up front; finalizers zero + commit
+    step.overlap_append = bool(overlap)
+    from kernels import cuda_ops as _ops
+
+    _ops.set_fused_copy_all(copy_all)
     exp_k, exp_v = to_np(arena.k).copy(), to_np(arena.v).copy()
     lens = np.full(B, L, np.int32)
     if use_graph:
@@ -313,3 +317,5 @@ def test_append_overlapping_the_verify_tail(use_graph, overlap):
         np.testing.assert_array_equal(to_np(arena.k), exp_k)
         np.testing.assert_array_equal(to_np(arena.v), exp_v)
         assert int(step.seq_ready.sum()) == 0  # re-armed
+        assert int(arena.group_counters().sum()) == 0
+    _ops.set_fused_copy_all(False)
