@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=CFG["B"], help="sequences per GPU")
     ap.add_argument("--force-fuse", action="store_true", help="N>1: keep the fused verify+append launch")
     ap.add_argument("--no-fuse", action="store_true", help="two launches per step (verify, kv_append) instead of sd_verify_append")
+    ap.add_argument("--no-zero-rejected", action="store_true",
+                    help="evidence runs: rollback = length update only, rejected slots are not zeroed (not the reference's semantics)")
     ap.add_argument("--copy-all", action="store_true", help="fused launch, copy-all mode (append CTAs copy all K+1 rows up front)")
     ap.add_argument("--interleave", action="store_true", help="fused launch: append CTAs of a sequence group right after its verify CTAs")
     ap.add_argument("--no-overlap", action="store_true",
@@ -309,7 +311,7 @@ def run_ours(args):
             # the whole step in ONE launch (sd_verify_append): verify CTAs, then append CTAs that wait per sequence
             arena.layer_table = tables[i]
             cuda_ops.verify_append_launch(st.logits, st.draft_ids, st.accept_len, st.accepted_mask, st.target_ids, st.bonus,
-                                          st.packed, st.workspace, st.seq_ready, arena, zero_rejected=True, exchange=px,
+                                          st.packed, st.workspace, st.seq_ready, arena, zero_rejected=not args.no_zero_rejected, exchange=px,
                                           exchange_push_in_append=args.exchange == "peer-kv")
             if exch is not None:
                 exch.all_gather(st.packed)
@@ -506,7 +508,7 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = load_peaks()
         verify_bytes = B * R * V * 2
-        kv_bytes = arena.step_bytes(mean_keep, R, True)
+        kv_bytes = arena.step_bytes(mean_keep, R, not args.no_zero_rejected)
         v_gbs = verify_bytes / (verify_ms * 1e-3) / 1e9
         kv_gbs = kv_bytes / (kv_ms * 1e-3) / 1e9
         attn_bytes = 2 * B * CFG["Hkv"] * (CFG["L"] + R) * CFG["D"] * 2 + 2 * B * CFG["Hq"] * R * CFG["D"] * 2
