@@ -8,9 +8,14 @@
  *
  * Conventions
  *   - All pointers are DEVICE pointers unless the name ends in _host.
- *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Nothing here
- *     allocates, synchronises or keeps global state: every call only enqueues work on `stream`,
- *     so calls are CUDA-graph capturable and callers keep ownership of every buffer.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  The compute entry points
+ *     (sd_verify_*, sd_kv_append*, sd_verify_attention, sd_sample_bonus, sd_exchange_wait) neither
+ *     allocate nor synchronise: every call only enqueues work on `stream`, so calls are CUDA-graph
+ *     capturable and callers keep ownership of every buffer.  Exceptions, none of them on the step:
+ *     sd_exchange_alloc / _open / _close / _free manage the peer-mapped exchange buffer (cudaMalloc +
+ *     CUDA IPC), and the sd_*_set_* hooks store process-wide tuning choices for evidence runs.
+ *   - sd_step_args, sd_exchange and sd_kv_layer are plain C structs (sd_exchange and the sd_kv_layer
+ *     table live in DEVICE memory, sd_step_args in host memory).
  *   - Return value: 0 = success; > 0 = a cudaError_t from the launch; < 0 = an sd_status
  *     argument error (nothing was enqueued).  sd_error_string() names either.
  *   - Strides are in ELEMENTS for logits / ids and in BYTES for KV tensors (stated per argument).
