@@ -435,13 +435,10 @@ template <typename T, int D, int MT, int KT, int STAGES>
 static cudaError_t launch_attn_cfg(const AttnParams& p, dim3 grid, cudaStream_t st) {
     constexpr int W = kAttnWarps;
     using SM = AttnSmem<D, MT, KT, STAGES, W>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(verify_attn_kernel<T, D, MT, KT, STAGES, W>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    // set on every call: the attribute is per device, and one process may drive several
+    cudaError_t e = cudaFuncSetAttribute(verify_attn_kernel<T, D, MT, KT, STAGES, W>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal);
+    if (e != cudaSuccess) return e;
     return launch_kernel(verify_attn_kernel<T, D, MT, KT, STAGES, W>, grid, dim3(W * 32), (size_t)SM::kTotal, st, p);
 }
 
