@@ -61,6 +61,10 @@ enum sd_accept_mode {
 };
 
 int sd_abi_version(void);
+/* sizeof / offsetof of the public structs, for bindings to check their mirror of the layout:
+ * 0 sizeof(sd_kv_layer), 1 sizeof(sd_exchange), 2 offsetof(sd_exchange, peer), 3 sizeof(sd_step_args),
+ * 4..7 offsetof(sd_step_args, layers | row_bytes | seq_lens | group_counters); other values -> 0. */
+size_t sd_struct_layout(int which);
 const char* sd_error_string(int code);
 /* Programmatic dependent launch for every kernel of the library (default on; env SD_B200_PDL=0 turns
  * it off): a kernel's CTAs may become resident while the previous kernel on the stream drains, and

@@ -1,6 +1,7 @@
 // Library-level entry points: ABI version, error strings, device query.
 #include "sd_common.cuh"
 
+#include <stddef.h>
 #include <stdlib.h>
 
 namespace sd {
@@ -22,6 +23,21 @@ int sd_set_pdl(int enabled) {
 }
 
 int sd_abi_version(void) { return SD_ABI_VERSION; }
+
+// Layout self-description for foreign-function bindings: sizeof / selected offsetof of the public structs.
+size_t sd_struct_layout(int which) {
+    switch (which) {
+        case 0: return sizeof(sd_kv_layer);
+        case 1: return sizeof(sd_exchange);
+        case 2: return offsetof(sd_exchange, peer);
+        case 3: return sizeof(sd_step_args);
+        case 4: return offsetof(sd_step_args, layers);
+        case 5: return offsetof(sd_step_args, row_bytes);
+        case 6: return offsetof(sd_step_args, seq_lens);
+        case 7: return offsetof(sd_step_args, group_counters);
+        default: return 0;
+    }
+}
 
 const char* sd_error_string(int code) {
     switch (code) {

@@ -29,6 +29,7 @@ _sz = C.c_size_t
 # name -> (restype, argtypes); must list every function include/sd_verify.h declares
 SIGNATURES = {
     "sd_abi_version": (_i, []),
+    "sd_struct_layout": (_sz, [_i]),
     "sd_error_string": (C.c_char_p, [_i]),
     "sd_set_pdl": (_i, [_i]),
     "sd_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),

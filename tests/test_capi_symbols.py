@@ -63,3 +63,19 @@ def test_sass_is_sm100a_and_uses_128bit_loads_and_tma():
     assert "HMNMX2.BF16_V2.NAN" in sass  # packed NaN-propagating bf16x2 max
     assert "REDUX.MAX" in sass           # warp reduce in hardware
     assert "UBLKCP" in sass  # cp.async.bulk (TMA 1-D) in the kv_append bulk variant
+
+
+def test_ctypes_mirrors_match_the_c_struct_layout():
+    """The ctypes Structures of kernels/_capi.py must have the layout the compiler gave the C structs."""
+    import ctypes as C
+
+    lib = _capi.lib()
+    assert lib.sd_struct_layout(0) == 4 * C.sizeof(C.c_void_p)
+    assert lib.sd_struct_layout(1) == C.sizeof(_capi.ExchangeDesc)
+    assert lib.sd_struct_layout(2) == _capi.ExchangeDesc.peer.offset
+    assert lib.sd_struct_layout(3) == C.sizeof(_capi.StepArgs)
+    assert lib.sd_struct_layout(4) == _capi.StepArgs.layers.offset
+    assert lib.sd_struct_layout(5) == _capi.StepArgs.row_bytes.offset
+    assert lib.sd_struct_layout(6) == _capi.StepArgs.seq_lens.offset
+    assert lib.sd_struct_layout(7) == _capi.StepArgs.group_counters.offset
+    assert lib.sd_struct_layout(99) == 0
