@@ -259,7 +259,7 @@ def run_ours(args):
     if world > 1 and not args.force_fuse:
         args.no_fuse = True
         args.no_overlap = True
-    if args.exchange == "peer":
+    if args.exchange == "peer" and not args.force_fuse:
         args.no_fuse = True
     B, K, V, NB = args.batch, CFG["K"], CFG["V"], CFG["nbuf"]
     R = K + 1

@@ -30,6 +30,8 @@
 // Exact torch.argmax semantics (first maximal index; NaN maximal, first NaN; -0 == +0) are kept
 // by (a) canonical-NaN propagating max, (b) folding -0 to +0 once per vector, (c) tie-breaking
 // every reduction level on the smallest position.
+#include <stdlib.h>
+
 #include "sd_kv_col.cuh"
 
 namespace sd {
@@ -1257,8 +1259,9 @@ int sd_verify_append(const sd_step_args* a, void* stream) {
     if (!a->seq_ready || !a->accept_len) return SD_ERR_INVALID_ARG;
     // With an exchange, the records must be pushed by the append part: the combination "verify finalizers
     // push + append part gathers" inside ONE grid hung at N = 8 (round 1, gpurun_out/bench19.log) and is
-    // refused until it is understood; use the two-launch form for it.
-    if (a->exchange && !a->exchange_push_in_append) return SD_ERR_UNSUPPORTED;
+    // refused until it is understood (it runs at N = 2; SD_B200_ALLOW_FUSED_VERIFY_PUSH=1 lifts the refusal for
+    // experiments); use the two-launch form for it.
+    if (a->exchange && !a->exchange_push_in_append && !getenv("SD_B200_ALLOW_FUSED_VERIFY_PUSH")) return SD_ERR_UNSUPPORTED;
     if (a->exchange && !a->packed) return SD_ERR_INVALID_ARG;
     if (a->B <= 0) return SD_OK;
     KvParams kp;
