@@ -191,7 +191,21 @@ SD_DEVINL void kv_col_body(const KvParams& p, const int cta_x, const int layer) 
     // Fused result exchange (multi-GPU): CTA (0,0) -- which pushed this rank's records at its start when
     // exchange_packed is set -- gathers every rank's records of the epoch once its own rows are copied:
     // the NVLink round trips overlap the rest of the append instead of trailing it.
-    if (p.xchg && cta_x == 0 && layer == 0) exchange_gather_cta(p.xchg, p.xchg_out);
+    if (p.xchg && cta_x == 0 && layer == 0) {
+#ifndef SD_REPRO_EPOCH_RACE  // (tools/repro_epoch_race.py builds a copy without this wait to show the stall)
+        if (p.seq_ready && !p.xchg_packed) {
+            // The records are pushed by the verify finalizers, which read the epoch from the exchange header and
+            // may still be running (this CTA only waited for ITS sequences).  The gather ends by advancing the
+            // epoch, so every local finalizer must have read it first -- it raises its flag after the push.
+            // lag = 0 implies this (the gather waits for the rank's own records); lag = 1 does not: without
+            // this wait a late finalizer tags its record with the NEXT epoch and the step after hangs.
+            for (int bb = threadIdx.x; bb < p.B; bb += blockDim.x)
+                while (ld_flag(p.seq_ready + bb) == 0) __nanosleep(100);
+            __syncthreads();
+        }
+#endif
+        exchange_gather_cta(p.xchg, p.xchg_out);
+    }
     retire_and_commit(p);
 }
 

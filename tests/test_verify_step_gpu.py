@@ -1,10 +1,13 @@
 """GPU: the batched verify step (verify -> kv_append), eager and as a replayed CUDA graph."""
+import time
+
 import numpy as np
 import pytest
 import torch
 
 from oracle import c_oracle
 from oracle import specdec_oracle as O
+from kernels import cuda_ops
 from specdec.cache.kv_arena import KVArena
 from specdec.verify_step import VerifyStep
 from helpers import make_verify_inputs, to_np
@@ -319,3 +322,55 @@ def test_append_overlapping_the_verify_tail(use_graph, overlap):
         assert int(step.seq_ready.sum()) == 0  # re-armed
         assert int(arena.group_counters().sum()) == 0
     _ops.set_fused_copy_all(False)
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_fused_launch_with_finalizer_push_and_one_step_lag(world, monkeypatch):
+    """Fused launch, records pushed by the verify finalizers, lag = 1: the gathering append CTA must not advance
+    the epoch before every finalizer of the same launch has read it (the round-1 multi-GPU stall,
+    tools/repro_epoch_race.py).  Many steps at a size where finalizers are still running when the first append
+    CTA is done."""
+    from scheduler.batch_shard import PeerExchange
+
+    monkeypatch.setenv("SD_B200_ALLOW_FUSED_VERIFY_PUSH", "1")
+    K, V, layers, H, D, L = 4, 32000, 4, 8, 128, 7
+    global_batch = 48 * world
+    xs = PeerExchange.emulate(world, global_batch, K, "cuda", lag=1)
+    try:
+        arenas, steps = [], []
+        for x in xs:
+            n = x.shard.local_batch
+            a = KVArena(layers, n, H, D, L + 5 * 40, K + 1, torch.bfloat16, "cuda")
+            a.set_lengths([L] * n)
+            a.new_k.normal_()
+            a.new_v.normal_()
+            arenas.append(a)
+            steps.append(VerifyStep(n, K, V, arena=None))
+            x.out.fill_(-7)
+        prev = None
+        for it in range(40):
+            logits, ids = make_verify_inputs(global_batch, K + 1, K, V, "bf16", p_match=0.7, seed=900 + it, device="cuda")
+            for x, st, a in zip(xs, steps, arenas):
+                s, e = x.shard.bounds()
+                st.logits.copy_(logits[s:e])
+                st.draft_ids.copy_(ids[s:e])
+                cuda_ops.verify_append_launch(st.logits, st.draft_ids, st.accept_len, st.accepted_mask, st.target_ids,
+                                              st.bonus, st.packed, st.workspace, st.seq_ready, a, exchange=x,
+                                              exchange_push_in_append=False)
+            done = torch.cuda.Event()
+            done.record()
+            t0 = time.perf_counter()
+            while not done.query():
+                assert time.perf_counter() - t0 < 5.0, f"step {it} stalled"
+                time.sleep(0.001)
+            want = torch.cat([st.packed for st in steps]).cpu().numpy()
+            for r, x in enumerate(xs):
+                got = x.unpad(x.out).cpu().numpy()
+                if prev is None:
+                    assert (got == -7).all()
+                else:
+                    np.testing.assert_array_equal(got, prev, err_msg=f"rank {r} step {it}")
+            prev = want
+    finally:
+        for x in xs:
+            x.close()
