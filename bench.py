@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--tuning", default="", help="threads,vectors_per_thread for the verify kernel (sweeps)")
     ap.add_argument("--kv-variant", type=int, default=0)
     ap.add_argument("--batch", type=int, default=CFG["B"], help="sequences per GPU")
-    ap.add_argument("--force-fuse", action="store_true", help="N>1: keep the fused verify+append launch")
+    ap.add_argument("--force-fuse", action="store_true", help="(accepted for old command lines; the fused launch is the default at every N)")
     ap.add_argument("--no-fuse", action="store_true", help="two launches per step (verify, kv_append) instead of sd_verify_append")
     ap.add_argument("--no-zero-rejected", action="store_true",
                     help="evidence runs: rollback = length update only, rejected slots are not zeroed (not the reference's semantics)")
@@ -58,8 +58,9 @@ def parse_args():
     ap.add_argument("--interleave", action="store_true", help="fused launch: append CTAs of a sequence group right after its verify CTAs")
     ap.add_argument("--no-overlap", action="store_true",
                     help="kv_append waits for the whole verify grid (PDL) instead of per-sequence flags")
-    ap.add_argument("--exchange", default="peer-kv", choices=["peer-kv", "peer", "nccl"],
-                    help="N>1: fused peer-memory exchange in the verify kernel (default) or one NCCL all-gather per step")
+    ap.add_argument("--exchange", default="peer", choices=["peer-kv", "peer", "nccl"],
+                    help="N>1: peer-memory exchange, records pushed by the verify finalizers (peer, default) or by the first "
+                         "append CTA (peer-kv), or one NCCL all-gather per step (nccl)")
     return ap.parse_args()
 
 
@@ -252,15 +253,10 @@ def run_ours(args):
     if args.copy_all:
         cuda_ops.set_fused_copy_all(True)
 
-    # Launch structure per step (measured): one GPU -> the fused verify+append launch;
-    # several GPUs -> two launches with PDL, the append pushing this rank's records to the peers at its START
-    # (the NVLink round trip hides behind the copy) and gathering at the end.  With the per-sequence flags /
-    # the fused launch the push would only start once the last sequence is verified (N=8: 38.9 vs 37.0 us).
-    if world > 1 and not args.force_fuse:
-        args.no_fuse = True
-        args.no_overlap = True
-    if args.exchange == "peer" and not args.force_fuse:
-        args.no_fuse = True
+    # Launch structure per step (measured): ONE fused verify+append launch at every N.  With
+    # several GPUs the verify finalizers push their records to every rank as soon as a sequence is verified and
+    # the first append CTA gathers them (N=8: 34.8 us per step; two PDL-chained launches with the push at the
+    # start of the append: 37.0 us -- `--no-fuse --no-overlap --exchange peer-kv`).
     B, K, V, NB = args.batch, CFG["K"], CFG["V"], CFG["nbuf"]
     R = K + 1
     total_steps = args.steps + args.warmup
@@ -279,8 +275,8 @@ def run_ours(args):
         if args.exchange in ("peer", "peer-kv"):
             try:
                 peer = PeerExchange(shard, K, dev)
-                exchange_kind = ("peer-memory stores issued by the first CTA of kv_append, gathered by its last CTA" if args.exchange == "peer-kv"
-                                 else "peer-memory stores from the verify kernel, confirmed + gathered by the last CTA of kv_append")
+                exchange_kind = ("peer-memory stores issued by the first append CTA at its start, gathered by the same CTA" if args.exchange == "peer-kv"
+                                 else "peer-memory stores from the verify finalizers, confirmed + gathered by the first append CTA")
             except Exception as e:  # noqa: BLE001  (CUDA IPC unavailable in this container)
                 print(f"[rank {rank}] PeerExchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr, flush=True)
         ok = torch.tensor([1 if peer is not None else 0], device=dev)

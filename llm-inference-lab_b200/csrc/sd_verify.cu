@@ -1257,11 +1257,9 @@ int sd_verify_append(const sd_step_args* a, void* stream) {
     if (!a) return SD_ERR_INVALID_ARG;
     if (a->rows != a->K + 1) return SD_ERR_SHAPE;  // the append keeps accept_len + 1 of the K + 1 offered rows
     if (!a->seq_ready || !a->accept_len) return SD_ERR_INVALID_ARG;
-    // With an exchange, the records must be pushed by the append part: the combination "verify finalizers
-    // push + append part gathers" inside ONE grid hung at N = 8 (round 1, gpurun_out/bench19.log) and is
-    // refused until it is understood (it runs at N = 2; SD_B200_ALLOW_FUSED_VERIFY_PUSH=1 lifts the refusal for
-    // experiments); use the two-launch form for it.
-    if (a->exchange && !a->exchange_push_in_append && !getenv("SD_B200_ALLOW_FUSED_VERIFY_PUSH")) return SD_ERR_UNSUPPORTED;
+    // With an exchange the records are pushed either by the append part (exchange_push_in_append) or by the verify
+    // finalizers; in both cases the first append CTA gathers them, after every finalizer of this launch has read
+    // the epoch (sd_kv_col.cuh -- the missing wait was the multi-GPU stall of round 1, tools/repro_epoch_race.py).
     if (a->exchange && !a->packed) return SD_ERR_INVALID_ARG;
     if (a->B <= 0) return SD_OK;
     KvParams kp;

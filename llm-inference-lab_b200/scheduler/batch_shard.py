@@ -101,9 +101,11 @@ class PeerExchange:
     """Fused multi-GPU result exchange over peer memory (include/sd_verify.h, ``sd_exchange``).
 
     The verify kernel's sequence finalizer stores each packed record into EVERY rank's exchange buffer
-    (NVLink stores on CUDA-IPC mapped peer pointers) and counts it there; ``wait()`` enqueues the 1-CTA
-    kernel that spins on the local arrival counter, copies the gathered records out and advances the
-    device-side epoch.  No NCCL launch on the step (a NCCL all-gather costs ~15 us on a ~32 us step).
+    (NVLink stores on CUDA-IPC mapped peer pointers), every value in one 8-byte word tagged with the epoch.
+    The records are confirmed and gathered by the first CTA of the append that follows (fused launch or
+    ``KVArena.append(exchange=...)``), or by ``wait()`` -- a 1-CTA kernel -- for steps without an append; either
+    polls the tagged words, copies the table to ``out`` and advances the device-side epoch.  No NCCL launch on
+    the step (a NCCL all-gather costs ~20 us on a ~33 us step at N=8).
     Pass ``desc_ptr`` to ``cuda_ops.verify_launch(exchange=...)`` / ``VerifyStep(exchange=...)``.
 
     One ``wait()`` per verify launch, on every rank, in the same order (SPMD); both are graph-capturable.

@@ -95,7 +95,8 @@ class VerifyStep:
             cuda_ops.verify_append_launch(
                 lg, ids, self.accept_len, self.accepted_mask, self.target_ids, self.bonus, self.packed, self.workspace,
                 self.seq_ready, self.arena, zero_rejected=True, check_capacity=False,
-                exchange=self.exchange if self.exchange_wait else None)
+                exchange=self.exchange if self.exchange_wait else None,
+                exchange_push_in_append=False)  # finalizers push per sequence (N=8: 34.8 us vs 38.9 us per step)
             return
         cuda_ops.verify_launch(
             lg, ids, self.accept_len, self.accepted_mask, self.target_ids, self.bonus, self.packed, self.workspace,

@@ -325,14 +325,13 @@ def test_append_overlapping_the_verify_tail(use_graph, overlap):
 
 
 @pytest.mark.parametrize("world", [1, 2])
-def test_fused_launch_with_finalizer_push_and_one_step_lag(world, monkeypatch):
+def test_fused_launch_with_finalizer_push_and_one_step_lag(world):
     """Fused launch, records pushed by the verify finalizers, lag = 1: the gathering append CTA must not advance
     the epoch before every finalizer of the same launch has read it (the round-1 multi-GPU stall,
     tools/repro_epoch_race.py).  Many steps at a size where finalizers are still running when the first append
     CTA is done."""
     from scheduler.batch_shard import PeerExchange
 
-    monkeypatch.setenv("SD_B200_ALLOW_FUSED_VERIFY_PUSH", "1")
     K, V, layers, H, D, L = 4, 32000, 4, 8, 128, 7
     global_batch = 48 * world
     xs = PeerExchange.emulate(world, global_batch, K, "cuda", lag=1)
@@ -345,7 +344,7 @@ def test_fused_launch_with_finalizer_push_and_one_step_lag(world, monkeypatch):
             a.new_k.normal_()
             a.new_v.normal_()
             arenas.append(a)
-            steps.append(VerifyStep(n, K, V, arena=None))
+            steps.append(VerifyStep(n, K, V, arena=a, exchange=x))  # run(): ONE launch, finalizers push, append gathers
             x.out.fill_(-7)
         prev = None
         for it in range(40):
@@ -354,9 +353,12 @@ def test_fused_launch_with_finalizer_push_and_one_step_lag(world, monkeypatch):
                 s, e = x.shard.bounds()
                 st.logits.copy_(logits[s:e])
                 st.draft_ids.copy_(ids[s:e])
-                cuda_ops.verify_append_launch(st.logits, st.draft_ids, st.accept_len, st.accepted_mask, st.target_ids,
-                                              st.bonus, st.packed, st.workspace, st.seq_ready, a, exchange=x,
-                                              exchange_push_in_append=False)
+                if it % 2:
+                    st.run()
+                else:  # the same launch through the op
+                    cuda_ops.verify_append_launch(st.logits, st.draft_ids, st.accept_len, st.accepted_mask, st.target_ids,
+                                                  st.bonus, st.packed, st.workspace, st.seq_ready, a, exchange=x,
+                                                  exchange_push_in_append=False)
             done = torch.cuda.Event()
             done.record()
             t0 = time.perf_counter()
