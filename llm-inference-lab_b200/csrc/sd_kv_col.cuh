@@ -22,7 +22,7 @@ struct KvParams {
     int early_rows;  // column kernel: fetch the offered rows before griddepcontrol.wait
     int32_t* overflow;
     int32_t* ticket;
-    const sd_exchange* xchg;  // nullable: confirm + gather the verify records of this step (last CTA)
+    const sd_exchange* xchg;  // nullable: confirm + gather the verify records of this step (first CTA, once its own rows are copied)
     int32_t* xchg_out;
     const int32_t* xchg_packed;  // nullable: this launch also PUSHES the local records (first CTA, at its start)
     int32_t* seq_ready;          // nullable: per-sequence flags set by the verify kernel's finalizers; the column

@@ -110,7 +110,7 @@ class KVArena:
         (true in the verify step: target forward -> fused verify -> append), so the kernel may fetch
         them while the previous kernel drains (include/sd_verify.h, sd_kv_append).
         ``exchange``: a scheduler.batch_shard.PeerExchange whose records of this step are confirmed and
-        gathered (into ``exchange.out``) by the last CTA of this launch -- replaces ``exchange.wait()``.
+        gathered (into ``exchange.out``) by the first CTA of this launch -- replaces ``exchange.wait()``.
         ``exchange_packed``: this rank's packed [B, K+2] records; when given, the first CTA of this launch
         pushes them to the peers (then the verify launch must NOT carry the exchange).
         ``seq_ready``: the [B] int32 flag array that the verify launch just before received: the append then

@@ -134,7 +134,7 @@ def test_peer_exchange_emulated_ranks(world, global_batch):
 
 
 def test_peer_exchange_gathered_by_the_append_launch():
-    """Same exchange, but confirmed + gathered by the last CTA of kv_append (no wait launch): the table
+    """Same exchange, but confirmed + gathered by the first CTA of kv_append (no wait launch): the table
     lands in exchange.out, epochs advance, KV and lengths stay bit-exact."""
     from scheduler.batch_shard import PeerExchange
 

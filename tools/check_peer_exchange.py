@@ -106,13 +106,13 @@ def main():
     arena.set_lengths([1024] * B)
     lens0 = torch.full((B,), 1024, dtype=torch.int32, device=dev)
 
-    def step_fused():  # verify (pushes records) -> kv_append (last CTA confirms + gathers)
+    def step_fused():  # verify (pushes records) -> kv_append (first CTA confirms + gathers)
         st.exchange = peer
         st.run()
         arena.seq_lens.copy_(lens0)
         arena.append(st.accept_len, keep_bias=1, check_capacity=False, exchange=peer)
 
-    def step_fused_kv_push():  # verify (no exchange) -> kv_append: first CTA pushes, last CTA gathers
+    def step_fused_kv_push():  # verify (no exchange) -> kv_append: first CTA pushes at its start and gathers at its end
         st.exchange = None
         st.run()
         arena.seq_lens.copy_(lens0)
