@@ -547,7 +547,7 @@ def run_ours(args):
             # the timed region launches ONE kernel per step: the fused verify + append kernel is the dominant kernel
             step_bytes = verify_bytes + kv_bytes
             step_gbs = step_bytes / (step_ms * 1e-3) / 1e9
-            line["roofline"] = {"bound": "hbm", "kernel": "verify_append_kernel<bf16,5> (the whole step in one launch: fused verify + kv_append of 28 layers)",
+            line["roofline"] = {"bound": "hbm", "kernel": "verify_append_kernel<bf16,3> (the whole step in one launch: fused verify + kv_append of 28 layers)",
                                 "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
                                 "frac_of_8TBs_nominal": step_gbs / 8000.0, "traffic": traffic.get("verify_append_kernel"),
                                 "algorithmic_bytes": step_bytes, "us_per_launch": step_ms * 1e3, "peak_source": peak_src,
