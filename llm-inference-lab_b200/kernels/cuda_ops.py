@@ -492,13 +492,14 @@ def verify_append_launch(
     zero_rejected: bool = True,
     check_capacity: bool = False,
     exchange=None,
-    exchange_push_in_append: bool = True,
+    exchange_push_in_append: bool = False,
 ) -> None:
     """The whole greedy verify step in ONE launch (sd_verify_append): fused verify over ``logits``
     [B,K+1,V] + kv_append of ``arena``'s staged rows for every layer (accept_len + 1 rows kept).  ``arena`` is a
     specdec.cache.kv_arena.KVArena; ``exchange`` a scheduler.batch_shard.PeerExchange (its records are pushed by
-    the append part when ``exchange_push_in_append`` else by the verify finalizers, and gathered by the append
-    part into ``exchange.out``)."""
+    the verify finalizers, each as soon as its sequence is verified -- or, with ``exchange_push_in_append``, by
+    the first append CTA once all are final, measured slower -- and gathered by the append part into
+    ``exchange.out``)."""
     import ctypes as C
 
     B, rows, V = logits.shape
