@@ -76,6 +76,7 @@ def make_logits(B, rows, V, dtype, kind, seed):
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-time", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="a handful of bf16 cases only")
     a = ap.parse_args()
     build()
     f = load()
@@ -85,6 +86,9 @@ def main() -> int:
             for kind in ("randn", "ties", "flat", "peaked"):
                 for (T, k, p_) in ((0.7, 50, 0.9), (1.0, 1, 1.0), (1.3, 1024, 0.5), (0.7, 17, 1.0), (None, None, None)):
                     cases.append((dtype, B, V, kind, T, k, p_))
+    if a.quick:
+        cases = [(torch.bfloat16, B, V, kind, T, k, p_) for (B, V) in ((64, 128256), (5, 1000)) for kind in ("randn", "ties")
+                 for (T, k, p_) in ((0.7, 50, 0.9), (None, None, None))]
     bad = 0
     ran = 0
     for ci, (dtype, B, V, kind, T, k, p_) in enumerate(cases):
@@ -98,7 +102,7 @@ def main() -> int:
         want_kept = torch.zeros(B, dtype=torch.int32, device="cuda")
         cuda_ops.sample_bonus_cuda(logits, row_index=row_index, uniform=uniform, temperature=T or 1.0, top_k=k, top_p=p_,
                                    out=want, kept_count=want_kept)
-        for cluster in (1, 2, 4, 8):
+        for cluster in ((2, 8) if a.quick else (1, 2, 4, 8)):
             if not fits(V, cluster, dtype):
                 continue  # the slice does not fit in shared memory next to the scratch
             got = torch.full((B,), -5, dtype=torch.int32, device="cuda")
