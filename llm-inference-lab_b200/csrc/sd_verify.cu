@@ -1270,6 +1270,16 @@ int sd_verify_append(const sd_step_args* a, void* stream) {
                             a->accept_len, 1, a->zero_rejected, a->max_seq_len_host, a->overflow_flag, a->ticket, a->exchange,
                             a->exchange_out, a->exchange_push_in_append ? a->packed : nullptr, a->seq_ready, &kp, &gx, &rb);
     if (rc != SD_OK) return rc;
+    {
+        // Experiment switch (default off, next-round A/B): request the first rows of K and V BEFORE the per-sequence
+        // flag wait.  Legal in this launch -- the staged rows are its inputs -- and it takes one dependent round
+        // trip off every append CTA; the combination with the flags has no GPU test yet, hence not the default.
+        static const int early = [] {
+            const char* e = getenv("SD_B200_FUSED_EARLY_ROWS");
+            return (e && e[0] == '1') ? 1 : 0;
+        }();
+        kp.early_rows = early;
+    }
     return run_verify(false, a->logits, a->logit_dtype, a->stride_b, a->stride_r, a->draft_ids, a->id_dtype, a->id_stride_b,
                       SD_ACCEPT_GREEDY, 0.f, 1.f, a->accept_len, a->accepted_mask, a->target_ids, a->bonus, a->packed, nullptr,
                       nullptr, nullptr, a->workspace, a->workspace_bytes, a->B, a->rows, a->K, a->V, stream,
