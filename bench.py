@@ -225,6 +225,32 @@ def workload_config(args, world):
     }
 
 
+def bind_to_gpu_numa_node(dev):
+    """Restrict this process to the CPUs of the GPU's NUMA node while the pinned staging buffers of the e2e leg are
+    allocated and first touched (first-touch placement puts them on that node: host->device copies then do not cross
+    the socket interconnect).  Returns (previous affinity, info dict) or (None, None) when the topology cannot be
+    read -- nothing is changed in that case."""
+    try:
+        pr = torch.cuda.get_device_properties(dev)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = Path("/sys/bus/pci/devices") / bdf
+        node = int((base / "numa_node").read_text().strip())
+        cpus = set()
+        for part in (base / "local_cpulist").read_text().strip().split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        prev = os.sched_getaffinity(0)
+        want = cpus & prev
+        if node < 0 or not want or want == prev:
+            return None, {"node": node, "bound": False}
+        os.sched_setaffinity(0, want)
+        return prev, {"node": node, "bound": True, "cpus": len(want)}
+    except Exception:  # noqa: BLE001  (no sysfs / no permission: leave the placement to the OS)
+        return None, None
+
+
 # ----------------------------------------------------------------------------------------- ours
 def run_ours(args):
     import torch.distributed as dist
@@ -445,6 +471,7 @@ def run_ours(args):
     if e2e_steps:
         arena.set_lengths([CFG["L"]] * B)
         e2e_graph = capture([lambda: one_step(0)])
+        prev_affinity, numa_info = bind_to_gpu_numa_node(dev)
         h_logits = [steps[i].logits.cpu().pin_memory() for i in range(2)]
         h_ids = [steps[i].draft_ids.cpu().pin_memory() for i in range(2)]
         h_k = [stage_k[i].cpu().pin_memory() for i in range(2)]
@@ -486,7 +513,12 @@ def run_ours(args):
             toks += e2e_step(s)
         barrier()
         t_e2e = time.perf_counter() - t0
-        e2e = {"tokens": toks, "seconds": t_e2e, "h2d": h2d, "d2h": d2h}
+        e2e = {"tokens": toks, "seconds": t_e2e, "h2d": h2d, "d2h": d2h, "numa": numa_info}
+        if prev_affinity is not None:
+            try:
+                os.sched_setaffinity(0, prev_affinity)  # the cpu_baseline leg uses every core
+            except Exception:  # noqa: BLE001
+                pass
 
     # ---- reduce over ranks: max time, summed tokens ----
     if world > 1:
@@ -556,7 +588,8 @@ def run_ours(args):
         if e2e:
             line["e2e"] = {"value": e2e_tokens_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
                            "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
-                           "api": "VerifyStep static buffers <- pinned host tensors; packed [B,K+2] record -> host"}
+                           "api": "VerifyStep static buffers <- pinned host tensors; packed [B,K+2] record -> host",
+                           "host_numa": e2e.get("numa")}
         if not args.no_cpu_baseline and world == 1:  # reported baseline: rank 0 at N=1 only
             cores = os.cpu_count() or 1
             tv, tk, reps = cpu_port_step_time(B, K, V, 2, CFG["Hkv"], CFG["D"], CFG["L"], 4, 3, cores)
