@@ -151,8 +151,23 @@ SD_DEVINL void kv_col_body(const KvParams& p, const int cta_x, const int layer) 
         }
         if (p.seq_ready) {
             // overlap with the verify kernel: sequence b's accept_len is final once its finalizer raised the flag
+#ifdef SD_FLAG_ACQUIRE  // next-round A/B (off): relaxed polling + ONE acquire load (LDG.STRONG.GPU + CCTL.IVALL) instead of
+                        // a volatile poll + __threadfence(), which adds MEMBAR.SC.GPU + ERRBAR per thread (5 % of the
+                        // fused step's stall samples under ncu)
+            for (;;) {
+                int f;
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(p.seq_ready + b) : "memory");
+                if (f != 0) break;
+                __nanosleep(100);
+            }
+            {
+                int f;
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(p.seq_ready + b) : "memory");
+            }
+#else
             while (ld_flag(p.seq_ready + b) == 0) __nanosleep(100);
             __threadfence();
+#endif
         }
         const int len = (p.seq_lens ? p.seq_lens[b] : 0) + (int)p.base_len;
         int n = keep_count(p, b);
