@@ -58,7 +58,7 @@ def cluster_sample(f, logits, row_index, uniform, temperature, top_k, top_p, clu
 def fits(V, cluster, dtype) -> bool:
     per = (V + cluster - 1) // cluster
     slice_ = (per + 7) & ~7
-    return 32 * 256 * 12 + 1024 * 8 + slice_ * (4 if dtype == torch.float32 else 2) <= 227 * 1024
+    return 32 * 256 * 12 + 1024 * 8 + slice_ * (4 if dtype == torch.float32 else 2) + 10240 <= 227 * 1024
 
 
 def make_logits(B, rows, V, dtype, kind, seed):
@@ -84,11 +84,12 @@ def main() -> int:
     for dtype in (torch.bfloat16, torch.float16, torch.float32):
         for (B, V) in ((64, 128256), (7, 50257), (5, 1000), (3, 37)):
             for kind in ("randn", "ties", "flat", "peaked"):
-                for (T, k, p_) in ((0.7, 50, 0.9), (1.0, 1, 1.0), (1.3, 1024, 0.5), (0.7, 17, 1.0), (None, None, None)):
+                for (T, k, p_) in ((0.7, 50, 0.9), (1.0, 1, 1.0), (1.3, 1024, 0.5), (0.7, 17, 1.0), (None, None, None),
+                                   (1.0, None, 0.9), (0.8, 5000, 0.95), (1.0, None, None), (0.5, 2000, None)):  # full-row path
                     cases.append((dtype, B, V, kind, T, k, p_))
     if a.quick:
         cases = [(torch.bfloat16, B, V, kind, T, k, p_) for (B, V) in ((64, 128256), (5, 1000)) for kind in ("randn", "ties")
-                 for (T, k, p_) in ((0.7, 50, 0.9), (None, None, None))]
+                 for (T, k, p_) in ((0.7, 50, 0.9), (None, None, None), (1.0, None, 0.9))]
     bad = 0
     ran = 0
     for ci, (dtype, B, V, kind, T, k, p_) in enumerate(cases):

@@ -10,10 +10,11 @@
 // pass.  The survivors are compacted, in index order, straight into the LEADER's shared memory, and the leader
 // finishes with exactly the code of the product kernel (nucleus_and_draw on a CompactRow).
 //
-// Contract: identical outputs to sd_sample_bonus for the configurations it accepts -- the greedy branch, and
-// sampling with 0 < top_k <= 1024, top_k < V (any top_p): the (tau, n_ties) prefix, the candidate list and its
-// order are the same, and all masses are fixed-point integers, so the token is bit-identical.  Other
-// configurations return SD_ERR_UNSUPPORTED (use sd_sample_bonus).
+// Contract: identical outputs to sd_sample_bonus for every configuration: the (tau, n_ties) prefixes, the candidate
+// list and its order are the same, and all masses are fixed-point integers (sums independent of their order), so
+// the token is bit-identical.  With 0 < top_k <= 1024 the leader finishes alone on the compacted candidates; with
+// no top-k or a larger one ("full-row path") the nucleus select, the kept mass and the draw also run across the
+// cluster, on the slices in shared memory.
 //
 // Build + check on a GPU box: experiments/sample_cluster/run_gpu.py.
 #include <cooperative_groups.h>
@@ -30,10 +31,13 @@ constexpr size_t kScratchBytes = (size_t)kSampWarps * kBins * (4 + 8) + (size_t)
 
 // What a CTA publishes for its peers (read through distributed shared memory after a cluster barrier).
 struct ClusterPub {
-    unsigned cnt[2][kBins];  // digit histogram of the slice, double-buffered over the radix passes
+    unsigned cnt[2][kBins];             // digit histogram of the slice, double-buffered over the radix passes
+    unsigned long long mass[2][kBins];  // ... and its fixed-point masses (by-mass select)
     uint32_t max_key;
     int max_pos;
-    unsigned ties, gt;       // elements of the slice with key == tau / key > tau
+    unsigned ties, gt;                  // elements of the slice with key == tau / key > tau
+    unsigned long long sum_mass;        // scratch of cluster_sum
+    unsigned sum_cnt;
 };
 
 // The slice of the row held in this CTA's shared memory, in the input type.
@@ -50,6 +54,314 @@ struct SliceRow {
         }
     }
 };
+
+// ---- full-row path: the building blocks of sd_sample.cuh restated over (slice in shared memory) x (cluster) ----
+
+// Sum of a (mass, count) pair over the cluster; `before` receives the sum over the lower ranks (index order).
+// Two cluster barriers: publish -> read, and read -> the next publish of the same fields.
+SD_DEVINL ScanPair cluster_sum(cg::cluster_group& cl, ClusterPub* pub, ScanPair mine, ScanPair& before, uint32_t* s_u32,
+                               unsigned long long* s_u64) {
+    const unsigned C = cl.num_blocks(), rank = cl.block_rank();
+    if (threadIdx.x == 0) {
+        pub->sum_mass = mine.mass;
+        pub->sum_cnt = mine.cnt;
+    }
+    cl.sync();
+    if (threadIdx.x == 0) {
+        ScanPair tot{0ull, 0u}, bef{0ull, 0u};
+        for (unsigned q = 0; q < C; ++q) {
+            const ClusterPub* pq = cl.map_shared_rank(pub, q);
+            const unsigned long long mq = pq->sum_mass;
+            const unsigned cq = pq->sum_cnt;
+            if (q < rank) {
+                bef.mass += mq;
+                bef.cnt += cq;
+            }
+            tot.mass += mq;
+            tot.cnt += cq;
+        }
+        s_u64[0] = tot.mass;
+        s_u64[1] = bef.mass;
+        s_u32[0] = tot.cnt;
+        s_u32[1] = bef.cnt;
+    }
+    __syncthreads();
+    ScanPair tot{s_u64[0], s_u32[0]};
+    before.mass = s_u64[1];
+    before.cnt = s_u32[1];
+    cl.sync();
+    return tot;
+}
+
+// Number of elements of the slice with key == tau, summed over the LOWER ranks: the row-wide tie rank at which this
+// slice starts (ties are kept in index order).  Only needed when the prefix keeps some, not all, of its ties.
+template <typename T>
+SD_DEVINL unsigned ties_before_slice(cg::cluster_group& cl, ClusterPub* pub, const SliceRow<T>& S, const SampShared& sh,
+                                     const SelectResult& sel, bool restricted) {
+    if (!restricted || sel.n_ties == kAllTies) return 0u;  // uniform over the cluster
+    unsigned my = 0;
+    for (int j = threadIdx.x; j < S.n; j += kSampThreads) my += order_key(to_float<T>(S.x[j])) == sel.tau ? 1u : 0u;
+    ScanPair v{0ull, my}, total, before;
+    block_exclusive_scan(v, total, sh.s_mass, sh.s_cnt);
+    cluster_sum(cl, pub, ScanPair{0ull, total.cnt}, before, sh.s_u32, sh.s_u64);
+    return before.cnt;
+}
+
+// for_each_kept of sd_sample.cuh over the slice, tie ranks starting at `ties_before`.
+template <typename T, typename Visit>
+SD_DEVINL void for_each_kept_slice(const SliceRow<T>& S, const SampShared& sh, const SelectResult& s, bool restricted,
+                                   unsigned ties_before, Visit&& visit) {
+    const int tid = threadIdx.x;
+    const bool rank_ties = restricted && s.n_ties != kAllTies;
+    unsigned run_ties = ties_before;
+    for (int t0 = 0; t0 < S.n; t0 += kTile) {
+        float xs[8];
+        bool ok[8];
+        S.load8(t0 + tid * 8, xs, ok);
+        bool keep[8];
+        uint32_t ks[8];
+        unsigned my_ties = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            ks[e] = order_key(xs[e]);
+            if (ok[e] && rank_ties && ks[e] == s.tau) ++my_ties;
+        }
+        unsigned rank = 0;
+        if (rank_ties) {
+            ScanPair v{0ull, my_ties}, total;
+            const ScanPair ex = block_exclusive_scan(v, total, sh.s_mass, sh.s_cnt);
+            rank = run_ties + ex.cnt;
+            run_ties += total.cnt;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            keep[e] = ok[e];
+            if (ok[e] && restricted) {
+                keep[e] = rank_ties ? in_prefix(ks[e], rank, s) : ks[e] >= s.tau;
+                if (rank_ties && ks[e] == s.tau) ++rank;
+            }
+        }
+        if (!visit(t0, xs, keep)) break;  // uniform across the CTA
+    }
+}
+
+// Kept mass and kept count of the prefix: this slice's (returned through `mine`), the lower ranks' (`before`) and
+// the cluster total (return value).
+template <typename T>
+SD_DEVINL ScanPair cluster_kept_mass(cg::cluster_group& cl, ClusterPub* pub, const SliceRow<T>& S, const SampShared& sh,
+                                     const SampleParams& p, float m, const SelectResult& sel, bool restricted,
+                                     unsigned ties_before, ScanPair& mine, ScanPair& before) {
+    unsigned long long mass = 0ull;
+    unsigned cnt = 0;
+    for_each_kept_slice(S, sh, sel, restricted, ties_before, [&](int, const float (&xs)[8], const bool (&keep)[8]) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (keep[e]) {
+                mass += fixed_mass(xs[e], m, p.inv_t_log2);
+                ++cnt;
+            }
+        return true;
+    });
+    ScanPair v{mass, cnt};
+    block_exclusive_scan(v, mine, sh.s_mass, sh.s_cnt);
+    return cluster_sum(cl, pub, mine, before, sh.s_u32, sh.s_u64);
+}
+
+// radix_select of sd_sample.cuh with the per-digit histograms summed over the cluster.  `pass_no` counts the
+// histogram passes of the whole kernel (double buffering of ClusterPub::cnt / mass).
+template <typename T>
+SD_DEVINL SelectResult cluster_radix_select(cg::cluster_group& cl, ClusterPub* pub, const SliceRow<T>& S,
+                                            const SampShared& sh, const SampleParams& p, float m, bool by_mass,
+                                            unsigned k_target, unsigned long long mass_target, const SelectResult outer,
+                                            bool has_outer, unsigned& pass_no) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned C = cl.num_blocks();
+    uint32_t prefix = 0u, prefix_mask = 0u;
+    unsigned cnt_above = 0;
+    unsigned long long mass_above = 0ull;
+    for (int d = 0; d < p.ndigits; ++d) {
+        const int shift = 24 - 8 * d;
+        const unsigned buf = pass_no & 1u;
+        ++pass_no;
+        for (int i = tid; i < kSampWarps * kBins; i += kSampThreads) {
+            sh.h_cnt[i] = 0u;
+            sh.h_mass[i] = 0ull;
+        }
+        __syncthreads();
+        for (int t0 = 0; t0 < S.n; t0 += kTile) {
+            float xs[8];
+            bool ok[8];
+            S.load8(t0 + tid * 8, xs, ok);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                unsigned bin = 0xffffffffu;
+                const uint32_t k = order_key(xs[e]);
+                if (ok[e] && !(has_outer && k < outer.tau) && (k & prefix_mask) == prefix) bin = (k >> shift) & 0xffu;
+                if (by_mass) {
+                    if (bin != 0xffffffffu) {
+                        atomicAdd(&sh.h_cnt[wid * kBins + bin], 1u);
+                        atomicAdd(&sh.h_mass[wid * kBins + bin], fixed_mass(xs[e], m, p.inv_t_log2));
+                    }
+                } else {
+                    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+                    if (bin != 0xffffffffu && lane == __ffs(peers) - 1)
+                        atomicAdd(&sh.h_cnt[wid * kBins + bin], __popc(peers));
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < kBins) {
+            unsigned c = 0;
+            unsigned long long w = 0ull;
+            for (int q = 0; q < kSampWarps; ++q) {
+                c += sh.h_cnt[q * kBins + tid];
+                w += sh.h_mass[q * kBins + tid];
+            }
+            pub->cnt[buf][tid] = c;
+            pub->mass[buf][tid] = w;
+        }
+        cl.sync();
+        if (tid < kBins) {
+            unsigned c = 0;
+            unsigned long long w = 0ull;
+            for (unsigned q = 0; q < C; ++q) {
+                const ClusterPub* pq = cl.map_shared_rank(pub, q);
+                c += pq->cnt[buf][tid];
+                w += pq->mass[buf][tid];
+            }
+            sh.tot_cnt[tid] = c;
+            sh.tot_mass[tid] = w;
+        }
+        __syncthreads();
+        if (has_outer && tid == 0 && (outer.tau & prefix_mask) == prefix && d == p.ndigits - 1) {
+            const unsigned bin = (outer.tau >> shift) & 0xffu;
+            if (sh.tot_cnt[bin] > outer.n_ties) {
+                const unsigned long long each = sh.tot_cnt[bin] ? sh.tot_mass[bin] / sh.tot_cnt[bin] : 0ull;
+                sh.tot_cnt[bin] = outer.n_ties;
+                sh.tot_mass[bin] = each * outer.n_ties;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned c = cnt_above;
+            unsigned long long w = mass_above;
+            int chosen = -1;
+            for (int bin = kBins - 1; bin >= 0; --bin) {
+                const unsigned c2 = c + sh.tot_cnt[bin];
+                const unsigned long long w2 = w + sh.tot_mass[bin];
+                const bool over = by_mass ? (w2 > mass_target) : (c2 > k_target);
+                if (sh.tot_cnt[bin] && over) {
+                    chosen = bin;
+                    break;
+                }
+                c = c2;
+                w = w2;
+            }
+            sh.s_u32[0] = (uint32_t)chosen;
+            sh.s_u32[1] = c;
+            sh.s_u64[0] = w;
+        }
+        __syncthreads();
+        const int chosen = (int)sh.s_u32[0];
+        cnt_above = sh.s_u32[1];
+        mass_above = sh.s_u64[0];
+        __syncthreads();
+        if (chosen < 0) {  // uniform over the cluster: every CTA walked the same totals
+            SelectResult all;
+            all.tau = has_outer ? outer.tau : 0u;
+            all.n_ties = has_outer ? outer.n_ties : kAllTies;
+            return all;
+        }
+        prefix |= (uint32_t)chosen << shift;
+        prefix_mask |= 0xffu << shift;
+    }
+    SelectResult res;
+    const uint32_t low_mask = ~prefix_mask;
+    res.tau = (prefix & 0x80000000u) ? prefix : (prefix | low_mask);
+    if (tid == 0) {
+        unsigned t = sh.tot_cnt[(prefix >> (24 - 8 * (p.ndigits - 1))) & 0xffu];
+        if (has_outer && res.tau == outer.tau && t > outer.n_ties) t = outer.n_ties;
+        unsigned keep;
+        if (by_mass) {
+            const unsigned long long each = fixed_mass(key_to_float(res.tau), m, p.inv_t_log2);
+            const unsigned long long room = mass_target > mass_above ? mass_target - mass_above : 0ull;
+            const unsigned long long fit = each ? room / each : (unsigned long long)t;
+            keep = fit > t ? t : (unsigned)fit;
+            if (cnt_above == 0 && keep == 0) keep = 1;
+        } else {
+            keep = k_target > cnt_above ? k_target - cnt_above : 0u;
+            if (keep > t) keep = t;
+        }
+        sh.s_u32[3] = keep == t ? kAllTies : keep;
+    }
+    __syncthreads();
+    res.n_ties = sh.s_u32[3];
+    __syncthreads();
+    return res;
+}
+
+// nucleus_and_draw of sd_sample.cuh across the cluster.  The CTA whose slice holds the target mass writes the token.
+template <typename T>
+SD_DEVINL void cluster_nucleus_and_draw(cg::cluster_group& cl, ClusterPub* pub, const SliceRow<T>& S, const SampShared& sh,
+                                        const SampleParams& p, float m, SelectResult sel, bool has_sel, float u, int b,
+                                        int amax, unsigned& pass_no) {
+    const int tid = threadIdx.x;
+    const unsigned C = cl.num_blocks(), rank = cl.block_rank();
+    ScanPair mine, before;
+    unsigned tb = ties_before_slice(cl, pub, S, sh, sel, has_sel);
+    if (p.top_p < 1.0f) {
+        const ScanPair z1 = cluster_kept_mass(cl, pub, S, sh, p, m, sel, has_sel, tb, mine, before);
+        const unsigned long long target = (unsigned long long)((double)p.top_p * (double)z1.mass);
+        SelectResult nucleus = cluster_radix_select(cl, pub, S, sh, p, m, true, 0u, target, sel, has_sel, pass_no);
+        if (has_sel && nucleus.tau == sel.tau && nucleus.n_ties > sel.n_ties) nucleus.n_ties = sel.n_ties;
+        sel = nucleus;
+        has_sel = true;
+        tb = ties_before_slice(cl, pub, S, sh, sel, has_sel);
+    }
+    const ScanPair z = cluster_kept_mass(cl, pub, S, sh, p, m, sel, has_sel, tb, mine, before);
+    u = u < 0.f ? 0.f : (u > 0.99999994f ? 0.99999994f : u);
+    const unsigned long long target = (unsigned long long)((double)u * (double)z.mass);
+    // the slice that holds the target (the last rank also takes a target that rounding left past the end)
+    const bool owner = before.mass <= target && (target < before.mass + mine.mass || rank == C - 1);
+    if (owner) {  // uniform within the CTA
+        if (tid == 0) sh.s_u32[0] = 0xffffffffu;
+        __syncthreads();
+        unsigned long long run_mass = before.mass;
+        for_each_kept_slice(S, sh, sel, has_sel, tb, [&](int t0, const float (&xs)[8], const bool (&keep)[8]) {
+            unsigned long long w[8];
+            unsigned long long my = 0ull;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                w[e] = keep[e] ? fixed_mass(xs[e], m, p.inv_t_log2) : 0ull;
+                my += w[e];
+            }
+            ScanPair v{my, 0u}, total;
+            const ScanPair ex = block_exclusive_scan(v, total, sh.s_mass, sh.s_cnt);
+            const unsigned long long bef = run_mass + ex.mass;
+            if (bef <= target && target < bef + my) {  // exactly one thread owns the target
+                unsigned long long c = bef;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (w[e] && target < c + w[e]) {
+                        sh.s_u32[0] = (uint32_t)(S.base + t0 + tid * 8 + e);
+                        break;
+                    }
+                    c += w[e];
+                }
+            }
+            run_mass += total.mass;
+            __syncthreads();
+            return sh.s_u32[0] == 0xffffffffu;
+        });
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t token = sh.s_u32[0];
+            p.out[b] = token == 0xffffffffu ? amax : (int)token;
+            if (p.kept_count) p.kept_count[b] = (int)z.cnt;
+        }
+    }
+    cl.sync();  // no CTA leaves while a peer may still read its ClusterPub
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kSampThreads, 1) sample_cluster_kernel(const SampleParams p, const int slice) {
@@ -170,6 +482,20 @@ __global__ void __launch_bounds__(kSampThreads, 1) sample_cluster_kernel(const S
     }
     const float m = key_to_float(kmax);
     const unsigned k_target = (unsigned)p.top_k;
+    unsigned pass_no = 0;
+    if (!(p.top_k > 0 && p.top_k < V && p.top_k <= kCompactCap)) {
+        // ---- full-row path: no top-k, or more survivors than the compacted list holds ----
+        SelectResult sel;
+        sel.tau = 0u;
+        sel.n_ties = kAllTies;
+        bool has_sel = false;
+        if (p.top_k > 0 && p.top_k < V) {
+            sel = cluster_radix_select(cl, &pub, S, sh, p, m, false, k_target, 0ull, sel, false, pass_no);
+            has_sel = true;
+        }
+        cluster_nucleus_and_draw(cl, &pub, S, sh, p, m, sel, has_sel, p.uniform[b], b, amax, pass_no);
+        return;
+    }
 
     // ---- top-k: radix select by COUNT over the cluster (sd_sample.cuh radix_select, by_mass = false, no outer) ----
     uint32_t prefix = 0u, prefix_mask = 0u;
@@ -385,7 +711,6 @@ int sd_sample_bonus_cluster(const void* logits, int logit_dtype, int64_t stride_
     if (uniform && !(temperature > 0.f)) return SD_ERR_INVALID_ARG;
     if (!row_index && (row_const < 0 || row_const >= rows)) return SD_ERR_SHAPE;
     if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != kMaxCluster) return SD_ERR_INVALID_ARG;
-    if (uniform && !(top_k > 0 && top_k <= kCompactCap && top_k < V)) return SD_ERR_UNSUPPORTED;
     SampleParams p;
     p.logits = logits;
     p.stride_b = stride_b;
@@ -406,7 +731,8 @@ int sd_sample_bonus_cluster(const void* logits, int logit_dtype, int64_t stride_
     const int per = (V + cluster - 1) / cluster;
     const int slice = (per + 7) & ~7;  // multiple of 8 elements: 16-byte aligned slices for 2-byte types
     const size_t elt = logit_dtype == SD_F32 ? 4 : 2;
-    if (kScratchBytes + (size_t)slice * elt > 227u * 1024u) return SD_ERR_UNSUPPORTED;  // the slice must fit in shared memory
+    // the slice must fit in shared memory next to the scratch and ~10 KB of static arrays (ClusterPub, scan scratch)
+    if (kScratchBytes + (size_t)slice * elt + 10240u > 227u * 1024u) return SD_ERR_UNSUPPORTED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     cudaError_t e;
     if (logit_dtype == SD_F32) e = launch_cluster<float>(p, B, cluster, slice, st);
