@@ -12,7 +12,8 @@ truth the GPU parity tests compare against (tests/test_golden_gpu.py).
 Sources executed (relative to /root/reference):
   src/kernels/reference.py            verify_prefix_ref, kv_append_ref, kv_append_with_mask_ref
   src/specdec/policies/policies.py    Typical / ConfidenceThreshold / TopKAgreement / LongestPrefix
-  src/specdec/core/pipeline.py        sample_bonus_token_from_logits (greedy branch)
+  src/specdec/core/pipeline.py        sample_bonus_token_from_logits (greedy branch; sampling branch: the
+                                      distribution handed to torch.multinomial)
   src/specdec/cache/kv_cache_manager.py  SafeKVCacheManager.realign_kv_cache
   src/specdec/cache/kv_types.py       KVCache.slice_prefix
 Inputs are seeded (1234 = the reference's default seed, pipeline.py:407).  bf16
@@ -256,11 +257,59 @@ def policy_cases():
     return len(names)
 
 
+# ----------------------------------------------------------------------------- bonus sampler, do_sample=True
+def sampler_cases():
+    """The sampling branch of sample_bonus_token_from_logits (pipeline.py:90-133) returns only the drawn token, and
+    the draw depends on torch's RNG stream.  What CAN be pinned is the distribution it draws from: torch.multinomial
+    is wrapped for the duration of the call (the reference function itself runs unmodified) and the `probs` tensor
+    the reference hands to it -- temperature, top-k, top-p and softmax applied -- is recorded."""
+    g = torch.Generator().manual_seed(SEED + 3)
+    real = torch.multinomial
+    seen = {}
+
+    def spy(probs, num_samples, *a, **k):
+        seen["probs"] = probs.detach().clone()
+        return real(probs, num_samples, *a, **k)
+
+    out, names = {}, []
+    settings = [(0.7, 50, 0.9), (1.0, None, 0.9), (1.3, 5, None), (0.5, 200, 0.5), (1.0, None, None), (2.0, 1, 0.1),
+                (0.7, 5000, 0.95)]
+    i = 0
+    for V, sharp, quantised in [(50, 2.0, False), (1000, 4.0, False), (50257, 3.0, False), (1000, 3.0, True)]:
+        for (T, k, p_) in settings:
+            row = torch.randn(V, generator=g) * sharp
+            if quantised:  # many exact ties, also across the top-k / top-p boundaries
+                row = torch.round(row * 2.0) / 2.0
+            torch.manual_seed(SEED + i)
+            torch.multinomial = spy
+            try:
+                tok = sample_bonus_token_from_logits(row, temperature=T, do_sample=True, top_p=p_, top_k=k, vocab_size=V)
+            finally:
+                torch.multinomial = real
+            name = f"samp{i}"
+            out[f"{name}.row"] = row.numpy().copy()
+            out[f"{name}.T"] = np.array([T], np.float32)
+            out[f"{name}.k"] = np.array([k if k is not None else 0], np.int32)
+            out[f"{name}.p"] = np.array([p_ if p_ is not None else 1.0], np.float32)
+            out[f"{name}.probs"] = seen["probs"].reshape(-1).numpy().astype(np.float32)
+            out[f"{name}.token"] = tok.numpy().astype(np.int32)
+            out[f"{name}.ties"] = np.array([int(quantised)], np.int32)
+            names.append(name)
+            i += 1
+    out["__cases__"] = np.array(names)
+    np.savez_compressed(OUT / "sampler.npz", **out)
+    return len(names)
+
+
 if __name__ == "__main__":
     torch.manual_seed(SEED)
+    if "--only-sampler" in sys.argv:
+        print(f"sampler cases: {sampler_cases()}")
+        sys.exit(0)
     nv = verify_cases()
     nk, nr = kv_cases()
     npol = policy_cases()
+    ns = sampler_cases()
     sizes = {p.name: p.stat().st_size for p in OUT.glob("*.npz")}
-    print(f"verify cases: {nv}; kv cases: {nk}; realign cases: {nr}; policy cases: {npol}")
+    print(f"verify cases: {nv}; kv cases: {nk}; realign cases: {nr}; policy cases: {npol}; sampler cases: {ns}")
     print(sizes)

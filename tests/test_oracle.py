@@ -200,6 +200,40 @@ def test_policies_match_reference(golden_dir):
         assert bonus[0] == z[f"{name}.bonus_greedy"][0]
 
 
+def test_bonus_sampler_distribution_matches_reference(golden_dir):
+    """do_sample=True: the distribution the reference hands to torch.multinomial (recorded by
+    tests/golden/make_golden.py through a wrapper around torch.multinomial, pipeline.py:90-133) equals
+    softmax(bonus_logits_filter(...)): same support, probabilities to fp32 rounding.  With exact ties across the
+    nucleus boundary torch.sort's (unstable) order decides WHICH of the equal logits survive; the oracle and the
+    kernel keep the lowest indices -- there the kept VALUES (sorted probabilities) and the support size must match."""
+    z = np.load(golden_dir / "sampler.npz")
+    n_exact = 0
+    for name in z["__cases__"]:
+        name = str(name)
+        row = z[f"{name}.row"]
+        T = float(z[f"{name}.T"][0])
+        k = int(z[f"{name}.k"][0]) or None
+        p = float(z[f"{name}.p"][0])
+        p = None if p >= 1.0 else p
+        ref = z[f"{name}.probs"]
+        x = O.bonus_logits_filter(row, T, k, p)
+        e = np.exp((x - x.max()).astype(np.float64))
+        probs = e / e.sum()
+        assert np.isfinite(x).sum() == (ref > 0).sum(), name
+        assert ref[int(z[f"{name}.token"][0])] > 0, name  # the token the reference drew lies in its own support
+        if np.array_equal(np.isfinite(x), ref > 0):
+            np.testing.assert_allclose(probs, ref, rtol=2e-5, atol=1e-7, err_msg=name)
+            n_exact += 1
+        else:
+            assert int(z[f"{name}.ties"][0]) == 1, f"{name}: support differs without ties in the row"
+            np.testing.assert_allclose(np.sort(probs), np.sort(ref), rtol=2e-5, atol=1e-7, err_msg=name)
+        # the inverse-CDF draw of the oracle lands inside the support for any u
+        for u in (0.0, 0.37, 0.999999):
+            tok, _ = O.sample_bonus(row, T, k, p, u)
+            assert np.isfinite(x[tok]), (name, u)
+    assert n_exact >= 26
+
+
 def test_bf16_roundtrip_helper():
     x = torch.randn(4096, generator=torch.Generator().manual_seed(0))
     x[0], x[1], x[2] = float("nan"), float("inf"), -0.0
