@@ -54,8 +54,8 @@ def parse_args():
     ap.add_argument("--no-fuse", action="store_true", help="two launches per step (verify, kv_append) instead of sd_verify_append")
     ap.add_argument("--no-zero-rejected", action="store_true",
                     help="evidence runs: rollback = length update only, rejected slots are not zeroed (not the reference's semantics)")
-    ap.add_argument("--copy-all", action="store_true", help="fused launch, copy-all mode (append CTAs copy all K+1 rows up front)")
-    ap.add_argument("--interleave", action="store_true", help="fused launch: append CTAs of a sequence group right after its verify CTAs")
+    ap.add_argument("--fused-mode", type=int, default=0, help="0 = lagged append (default), 1 = round-1 layout (append CTAs behind all verify CTAs)")
+    ap.add_argument("--lag", type=int, default=0, help="fused mode 0: sequences of lag (0 = heuristic)")
     ap.add_argument("--no-overlap", action="store_true",
                     help="kv_append waits for the whole verify grid (PDL) instead of per-sequence flags")
     ap.add_argument("--exchange", default="peer", choices=["peer-kv", "peer", "nccl"],
@@ -274,10 +274,8 @@ def run_ours(args):
         cuda_ops.set_verify_tuning(t, v)
     if args.kv_variant:
         cuda_ops.set_kv_variant(args.kv_variant)
-    if args.interleave:
-        cuda_ops._capi.lib().sd_verify_append_set_interleave(1)
-    if args.copy_all:
-        cuda_ops.set_fused_copy_all(True)
+    if args.fused_mode or args.lag:
+        cuda_ops.set_fused_mode(args.fused_mode, args.lag)
 
     # Launch structure per step (measured): ONE fused verify+append launch at every N.  With
     # several GPUs the verify finalizers push their records to every rank as soon as a sequence is verified and
@@ -331,7 +329,7 @@ def run_ours(args):
         st = steps[i]
         if not args.no_fuse:
             # the whole step in ONE launch (sd_verify_append): verify CTAs, then append CTAs that wait per sequence
-            arena.layer_table = tables[i]
+            arena.use_staging(stage_k[i], stage_v[i], tables[i])
             cuda_ops.verify_append_launch(st.logits, st.draft_ids, st.accept_len, st.accepted_mask, st.target_ids, st.bonus,
                                           st.packed, st.workspace, st.seq_ready, arena, zero_rejected=not args.no_zero_rejected, exchange=px,
                                           exchange_push_in_append=args.exchange == "peer-kv")
@@ -342,7 +340,7 @@ def run_ours(args):
         st.exchange = None if push_in_kv else px
         st.raise_flags = not args.no_overlap  # kv_append starts per sequence, overlapping the verify tail
         st.run()
-        arena.layer_table = tables[i]
+        arena.use_staging(stage_k[i], stage_v[i], tables[i])
         # N>1, peer exchange: the records are pushed to every rank by the verify finalizers ("peer") or by the
         # first CTA of the append ("peer-kv": the NVLink round trip hides behind the append); the last CTA of
         # the append confirms + gathers them (no launch of its own)
@@ -436,7 +434,7 @@ def run_ours(args):
         return a.elapsed_time(b) / n_launch
 
     def kv_only(i):
-        arena.layer_table = tables[i]
+        arena.use_staging(stage_k[i], stage_v[i], tables[i])
         arena.append(steps[i].accept_len, keep_bias=1, zero_rejected=True, check_capacity=False)
 
     for st in steps:  # the kernel alone: without the peer stores / per-sequence flags (both need the append after it)

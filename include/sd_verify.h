@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SD_ABI_VERSION 2
+#define SD_ABI_VERSION 3
 
 /* element type of logits / KV / attention tensors */
 enum sd_dtype { SD_F32 = 0, SD_F16 = 1, SD_BF16 = 2 };
@@ -63,7 +63,7 @@ enum sd_accept_mode {
 int sd_abi_version(void);
 /* sizeof / offsetof of the public structs, for bindings to check their mirror of the layout:
  * 0 sizeof(sd_kv_layer), 1 sizeof(sd_exchange), 2 offsetof(sd_exchange, peer), 3 sizeof(sd_step_args),
- * 4..7 offsetof(sd_step_args, layers | row_bytes | seq_lens | group_counters); other values -> 0. */
+ * 4..7 offsetof(sd_step_args, layers | row_bytes | seq_lens | step_state); other values -> 0. */
 size_t sd_struct_layout(int which);
 const char* sd_error_string(int code);
 /* Programmatic dependent launch for every kernel of the library (default on; env SD_B200_PDL=0 turns
@@ -72,6 +72,16 @@ const char* sd_error_string(int code);
 int sd_set_pdl(int enabled);
 /* Fills SM count and compute capability of the current device.  Returns 0 or a cudaError_t. */
 int sd_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Device-side waits are BOUNDED.  The kernels of this library wait across CTAs (a verify finalizer for the partial
+ * results of its rows, an append for a sequence's completion word) and across GPUs (the exchange gather for the
+ * peers' records, the start gate).  Every such poll gives up after 2 s of %globaltimer, records which kind of
+ * wait expired and lets the launch run to its end (its outputs are then garbage; accesses stay in bounds), so a dead
+ * peer, a stale workspace or a violated dispatch-order assumption (see sd_verify_append) surfaces here as a code
+ * instead of a hung GPU.  sites_out (nullable) receives the OR of: 1 partial slots, 2 sequence word / flag,
+ * 4 all-sequence wait, 8 peer words, 16 start gate; 0 = no wait has expired since the last clear.  Reads device
+ * memory with a synchronising copy: call it at step boundaries / in error paths, not per launch.
+ * Returns 0 or a cudaError_t. */
+int sd_device_error(int clear, unsigned* sites_out);
 
 /* ------------------------------------------------------------------------------------------
  * Multi-GPU result exchange over peer memory (batch-sharded step, one process per GPU).
@@ -285,17 +295,25 @@ int sd_kv_append_layer(void* arena_k, void* arena_v, const void* new_k, const vo
 /* ------------------------------------------------------------------------------------------
  * The whole verify step in ONE launch: fused verify (greedy) + kv_append of all layers.
  *
- * Same results as sd_verify_prefix(rows = K + 1, seq_ready) followed by sd_kv_append(n_keep =
- * accept_len, keep_bias = 1, seq_lens in place, seq_ready), i.e. the reference's per-sequence
- * accept / bonus / append block (src/specdec/core/pipeline.py:2958-3620 for the arithmetic part) --
- * but the append CTAs are part of the verify grid (dispatched after the verify CTAs, waiting on the
- * per-sequence flags), so a step pays one launch, one ramp and one tail instead of two.
- * Requirements: greedy acceptance, unmasked 16-byte aligned KV rows (the column kernel), the
- * bulk-chunk verify variant (the default); otherwise SD_ERR_UNSUPPORTED: issue the two launches.
- * With `exchange`, the records are pushed by the verify finalizers, each as soon as its sequence is
- * verified (exchange_push_in_append == 0, the faster form: 34.8 us per step at 8 GPUs), or by the first
- * append CTA once all of them are final (exchange_push_in_append != 0, 38.9 us); in both forms the first
- * append CTA gathers every rank's records into exchange_out and advances the epoch -- only after every
+ * Same results as sd_verify_prefix(rows = K + 1) followed by sd_kv_append(n_keep = accept_len, keep_bias = 1,
+ * seq_lens in place), i.e. the reference's per-sequence accept / bonus / append block
+ * (src/specdec/core/pipeline.py:2958-3620 for the arithmetic part; rollback semantics
+ * src/kernels/reference.py:133-157: kept rows compacted after the valid ones, rejected slots zero).
+ *
+ * Default layout ("lagged append"): every verify CTA reduces one chunk of one logits row AND carries one piece of
+ * the append of the sequence `lag` places earlier in the batch -- requested while its own chunk is in flight,
+ * stored after its partial result is published -- so the append traffic streams under the verify phase instead
+ * of behind it; a short tail of CTAs carries the pieces of the last `lag` sequences.  The finalizer of a
+ * sequence publishes ONE 8-byte word {launch tag, accept_len + 1, old length} in step_state and stores the new
+ * length; nothing is ever re-armed (words of earlier launches carry another tag).
+ * DISPATCH-ORDER REQUIREMENT: a CTA only waits for results of CTAs with a lower block index; the kernel relies on
+ * the hardware dispatching the blocks of a 1-D grid in index order (true of every CUDA GPU to date, not promised
+ * by the programming model).  All waits are bounded: see sd_device_error.
+ * Requirements: greedy acceptance, 16-byte aligned unmasked KV rows, the bulk-chunk verify variant (the default);
+ * otherwise SD_ERR_UNSUPPORTED: issue the two launches.
+ * With `exchange`, the records are pushed by the verify finalizers, each as soon as its sequence is verified
+ * (exchange_push_in_append == 0, the faster form), or by the first tail CTA once all of them are final; in both
+ * forms that CTA gathers every rank's records into exchange_out and advances the exchange epoch -- only after every
  * finalizer of the launch has read it.
  */
 typedef struct sd_step_args {
@@ -319,26 +337,31 @@ typedef struct sd_step_args {
     int64_t max_seq_len_host;
     int32_t* seq_lens;      /* updated in place */
     int32_t* overflow_flag; /* nullable */
-    int32_t* ticket;
-    int32_t* seq_ready;     /* [B] int32, zero before the launch, re-zeroed by it */
+    int32_t* ticket;        /* one int32, zero before the first launch (the kernel re-zeroes it) */
+    int32_t* seq_ready;     /* mode 1 only: [B] int32, zero before the launch, re-zeroed by it */
     /* multi-GPU exchange (nullable) */
     const sd_exchange* exchange;
     int32_t* exchange_out;
-    /* copy-all mode (sd_verify_append_set_copy_all): 2 * ceil(B * H * row_bytes / 16 / 256) uint32, zero before
-     * the first launch (the kernel re-zeroes them); nullable -> the flag-wait mode is used */
-    void* group_counters;
+    /* mode 0 (default): sd_step_state_bytes(B) bytes, 8-byte aligned, zero before the FIRST launch and never touched
+     * by the caller afterwards: u64 sequence words[B], u32 launch epoch, u32 reserved.  One state per stream of
+     * steps (launches that may overlap need their own). */
+    int32_t* step_state;
+    /* Optional (mode 0): uniform layers.  When either stride is non-zero, layer l's pointers are
+     * layer0.{arena_k, arena_v} + l * layer_stride_arena and layer0.{new_k, new_v} + l * layer_stride_new (bytes,
+     * multiples of 16) -- the layout of a KV cache allocated as ONE [layers, B, H, C, D] tensor -- and the device
+     * table `layers` is not read by the append part: a row request then depends on nothing but the thread index
+     * (no table lookup in front of it).  `layers` must still describe the same pointers. */
+    sd_kv_layer layer0;
+    int64_t layer_stride_arena, layer_stride_new;
 } sd_step_args;
 
+size_t sd_step_state_bytes(int B);
 int sd_verify_append(const sd_step_args* args, void* stream);
-/* Copy-all mode of sd_verify_append (off by default): the append CTAs copy ALL K+1 offered rows without waiting
- * for anything and sit in front of their sequences' verify CTAs in block order; each sequence's verify finalizer
- * then zeroes the rejected slots and advances the length.  Same results; +1 row-set of traffic for the rejected
- * rows (written twice), no serialised append phase.  Single-GPU only (SD_ERR_UNSUPPORTED with an exchange). */
-int sd_verify_append_set_copy_all(int enabled);
-/* Evidence runs: 0 (default) = all append CTAs after all verify CTAs; 1 = the append CTAs of a group of
- * sequences directly follow that group's verify CTAs in block order.  Measured on B200 the interleaved
- * order is slower (43 vs 34 us per step): the waiting append CTAs hold registers the verify CTAs need. */
-int sd_verify_append_set_interleave(int enabled);
+/* Layout of sd_verify_append: mode 0 (default) = lagged append, `lag` sequences (0 = heuristic: about 1.5 waves
+ * of resident CTAs); mode 1 = round-1 layout kept for A/B evidence: all append CTAs behind all verify CTAs, each
+ * thread waiting for its sequence's seq_ready flag -- the two phases serialise (34.6 us vs the sum of its parts
+ * 18.9 + 14.9 us at B = 64, K = 4, V = 128256, 28 layers). */
+int sd_verify_append_set_mode(int mode, int lag);
 
 /* Variant selector for sd_kv_append (evidence runs): 0 = heuristic, 1 = 128-bit LDG/STG kernel,
  * 2 = cp.async.bulk (TMA 1-D) shared-memory staged kernel, 3 = column kernel (one thread per 16-byte

@@ -34,7 +34,7 @@ size_t sd_struct_layout(int which) {
         case 4: return offsetof(sd_step_args, layers);
         case 5: return offsetof(sd_step_args, row_bytes);
         case 6: return offsetof(sd_step_args, seq_lens);
-        case 7: return offsetof(sd_step_args, group_counters);
+        case 7: return offsetof(sd_step_args, step_state);
         default: return 0;
     }
 }
@@ -52,6 +52,15 @@ const char* sd_error_string(int code) {
     }
     if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
     return "unknown sd_status";
+}
+
+int sd_device_error(int clear, unsigned* sites_out) {
+    unsigned a = 0u, b = 0u, c = 0u;
+    int rc = sd::verify_tu_spin_error(clear, &a);
+    if (rc == 0) rc = sd::kv_tu_spin_error(clear, &b);
+    if (rc == 0) rc = sd::exchange_tu_spin_error(clear, &c);
+    if (sites_out) *sites_out = a | b | c;
+    return rc;
 }
 
 int sd_device_info(int* sm_count, int* cc_major, int* cc_minor) {

@@ -46,6 +46,40 @@ SD_DEVINL unsigned long long global_timer_ns() {
     return t;
 }
 
+// ---- bounded device-side waits ------------------------------------------------------------------
+// Every cross-CTA / cross-GPU poll of this library (finalizer -> partial slots, append -> sequence
+// flags, gather -> peer words) goes through a SpinGuard: after kSpinBudgetNs of %globaltimer it gives
+// up, records WHAT it was waiting for in a per-translation-unit device word and lets the kernel run to
+// its end (results of that launch are garbage, memory accesses stay in bounds).  The host reads the
+// word with sd_device_error() (sd_api.cu) -- a dead peer, a stale workspace or a broken dispatch-order
+// assumption becomes an error code instead of an unkillable GPU.
+enum SpinSite : unsigned {
+    kSpinPartials = 1u,   // verify finalizer waiting for the partial slots of its rows
+    kSpinSeqFlag = 2u,    // append waiting for a sequence's completion flag
+    kSpinAllFlags = 4u,   // gather / last CTA waiting for every sequence flag of the launch
+    kSpinPeerWords = 8u,  // exchange gather waiting for a peer's tagged words
+    kSpinStartGate = 16u  // sd_exchange_start_gate waiting for the peers' arrival words
+};
+constexpr unsigned long long kSpinBudgetNs = 2000000000ull;  // 2 s: five orders of magnitude above any legitimate wait
+static __device__ unsigned g_spin_error = 0u;                // one copy per translation unit (no -rdc)
+
+struct SpinGuard {
+    unsigned long long t0 = 0ull;
+    unsigned polls = 0u;
+    // true = keep waiting; false = budget exhausted (error recorded)
+    SD_DEVINL bool keep_waiting(unsigned site) {
+        if ((++polls & 127u) != 0u) return true;
+        const unsigned long long now = global_timer_ns();
+        if (t0 == 0ull) {
+            t0 = now;
+            return true;
+        }
+        if (now - t0 < kSpinBudgetNs) return true;
+        atomicOr(&g_spin_error, site);
+        return false;
+    }
+};
+
 // ---- streaming global loads: read-once data must not displace the KV working set in L1 ----
 SD_DEVINL uint4 ldg_stream_v4(const void* p) {
     uint4 r;
@@ -227,7 +261,9 @@ SD_DEVINL void exchange_gather_cta(const sd_exchange* x, int32_t* out) {
             for (int u = 0; u < kU; ++u) {
                 if (!live[u]) continue;
                 const int i = i0 + u * blockDim.x;
+                SpinGuard guard;
                 while ((unsigned)(w[u] >> 32) != want) {
+                    if (!guard.keep_waiting(kSpinPeerWords)) break;
                     __nanosleep(64);
                     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w[u]) : "l"(words + i) : "memory");
                 }
@@ -238,6 +274,22 @@ SD_DEVINL void exchange_gather_cta(const sd_exchange* x, int32_t* out) {
     __syncthreads();
     if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(own) = epoch + 1u;
 }
+
+// host side: OR of the spin sites that ran out of budget in THIS translation unit's kernels since the last clear
+// (synchronises the device: not for the step path)
+static inline int tu_spin_error(int clear, unsigned* out) {
+    unsigned v = 0u;
+    cudaError_t e = cudaMemcpyFromSymbol(&v, g_spin_error, sizeof(v));
+    if (e == cudaSuccess && clear && v) {
+        const unsigned z = 0u;
+        e = cudaMemcpyToSymbol(g_spin_error, &z, sizeof(z));
+    }
+    *out = v;
+    return e == cudaSuccess ? 0 : (int)e;
+}
+int verify_tu_spin_error(int clear, unsigned* out);    // sd_verify.cu
+int kv_tu_spin_error(int clear, unsigned* out);        // sd_kv.cu
+int exchange_tu_spin_error(int clear, unsigned* out);  // sd_exchange.cu
 
 inline int elt_size(int dtype) { return dtype == SD_F32 ? 4 : 2; }
 

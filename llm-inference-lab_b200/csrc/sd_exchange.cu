@@ -12,6 +12,8 @@ __global__ void __launch_bounds__(256) exchange_wait_kernel(const sd_exchange* x
     exchange_gather_cta(x, out);
 }
 
+int exchange_tu_spin_error(int clear, unsigned* out) { return tu_spin_error(clear, out); }
+
 }  // namespace sd
 
 extern "C" {

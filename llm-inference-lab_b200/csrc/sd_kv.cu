@@ -232,6 +232,13 @@ int kv_prepare_col(const sd_kv_layer* layers, int n_layers, int B, int H, int R,
     p.xchg_packed = exchange_packed;
     p.seq_ready = seq_ready;
     p.fused = 1;
+    p.flags = nullptr;
+    p.epoch_word = nullptr;
+    p.lag = p.pieces = p.piece_items = p.seq_items = p.tail_pieces = p.eager_rows = p.l2_prefetch = p.uniform = p.stagger_ns = 0;
+    p.carry_ni = kCarryNI;
+    p.ls_arena = p.ls_new = 0;
+    p.layer0 = sd_kv_layer{nullptr, nullptr, nullptr, nullptr};
+    p.fd_vpr = p.fd_R = p.fd_H = make_fastdiv(1);
     if (!aligned_to(p, nullptr, 0, 16)) return SD_ERR_UNSUPPORTED;
     const int64_t slots = (int64_t)B * H * (row_bytes / 16);
     *grid_x = (unsigned)((slots + 255) / 256);
@@ -241,6 +248,8 @@ int kv_prepare_col(const sd_kv_layer* layers, int n_layers, int B, int H, int R,
     *out = p;
     return SD_OK;
 }
+
+int kv_tu_spin_error(int clear, unsigned* out) { return tu_spin_error(clear, out); }
 
 }  // namespace sd
 
@@ -302,6 +311,13 @@ static int kv_append_impl(const sd_kv_layer* layers, const sd_kv_layer* single, 
     p.xchg_packed = exchange_packed;
     p.seq_ready = seq_ready;
     p.fused = 0;
+    p.flags = nullptr;
+    p.epoch_word = nullptr;
+    p.lag = p.pieces = p.piece_items = p.seq_items = p.tail_pieces = p.eager_rows = p.l2_prefetch = p.uniform = p.stagger_ns = 0;
+    p.carry_ni = kCarryNI;
+    p.ls_arena = p.ls_new = 0;
+    p.layer0 = sd_kv_layer{nullptr, nullptr, nullptr, nullptr};
+    p.fd_vpr = p.fd_R = p.fd_H = make_fastdiv(1);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
     if (R == 0) {  // nothing offered: only the length commit (identity) is required

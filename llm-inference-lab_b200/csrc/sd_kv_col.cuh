@@ -5,6 +5,22 @@
 
 namespace sd {
 
+// n / d for n < 2^31 as one 64-bit multiply + shift (m = ceil(2^(31 + s) / d), s = ceil(log2 d); exact for 31-bit n)
+struct FastDiv {
+    uint32_t m, sh, d, pad;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    uint32_t s = 0;
+    while ((1ull << s) < d) ++s;
+    f.sh = 31 + s;
+    f.m = (uint32_t)(((1ull << f.sh) + d - 1) / d);
+    f.d = d;
+    f.pad = 0;
+    return f;
+}
+SD_DEVINL int fd_div(const FastDiv& f, int n) { return (int)(((unsigned long long)(unsigned)n * f.m) >> f.sh); }
+
 struct KvParams {
     const sd_kv_layer* layers;  // device table, or nullptr -> `single` (passed by value)
     sd_kv_layer single;
@@ -29,6 +45,23 @@ struct KvParams {
                                  // kernel then waits per sequence instead of for the whole previous grid
     unsigned total_ctas;
     int fused;  // 1 = running inside verify_append_kernel (grid-level wait already done)
+    // ---- lagged append (the default fused step, verify_step_kernel in sd_verify.cu) ----
+    unsigned long long* flags;  // [B] sequence words {tag:24 | n_keep:8 | old length:32}, written by the verify finalizers
+    unsigned* epoch_word;       // launch counter; tag = (epoch + 1) & 0xffffff
+    int lag;                    // the rows of sequence b are moved by the verify CTAs of sequence b + lag (clamped to B)
+    int pieces;                 // verify CTAs per sequence = pieces the append of one sequence is cut into
+    int piece_items, seq_items; // items per piece / per sequence; item = the K and the V vector of one (layer, h, row, 16-byte column)
+    int tail_pieces;            // tail CTAs per sequence
+    // uniform layers (optional): layer l's four pointers are layer0's + l * {ls_arena, ls_arena, ls_new, ls_new}; the
+    // device table is then never read -- an item's row request depends on nothing but the thread's index
+    sd_kv_layer layer0;
+    int64_t ls_arena, ls_new;
+    int uniform;
+    int carry_ni;               // items a carrying verify CTA parks per thread (1..kCarryNI)
+    int stagger_ns;             // A/B: first-wave CTAs delay their bulk copy by slot * stagger_ns
+    int l2_prefetch;            // verify CTAs of the last `lag` sequences pull their sequence's rows into L2 (default on)
+    int eager_rows;             // A/B: carrying CTAs fetch their rows without looking at the sequence word first
+    FastDiv fd_vpr, fd_R, fd_H; // item -> (column, row, head, layer) without integer division
 };
 
 SD_DEVINL int ld_flag(const int32_t* p) {
@@ -44,6 +77,17 @@ SD_DEVINL int keep_count(const KvParams& p, int b) {
         n = n < 0 ? 0 : (n > p.R ? p.R : n);
     }
     return n;
+}
+
+// whole CTA: wait until the verify finalizers have raised every sequence's flag (bounded)
+SD_DEVINL void wait_all_seq_ready(const KvParams& p) {
+    for (int bb = threadIdx.x; bb < p.B; bb += blockDim.x) {
+        SpinGuard guard;
+        while (ld_flag(p.seq_ready + bb) == 0) {
+            if (!guard.keep_waiting(kSpinAllFlags)) break;
+            __nanosleep(100);
+        }
+    }
 }
 
 // position of the j-th set bit of mask[b, 0..R) (reference.py:149-157), or -1
@@ -132,8 +176,7 @@ SD_DEVINL void kv_col_body(const KvParams& p, const int cta_x, const int layer) 
     if (!p.seq_ready && !p.fused) pdl_wait();  // (fused launch: the kernel waited at its top)
     if (p.xchg && p.xchg_packed && cta_x == 0 && layer == 0) {
         if (p.seq_ready) {  // the packed records of ALL sequences must be final before they are pushed
-            for (int bb = threadIdx.x; bb < p.B; bb += blockDim.x)
-                while (ld_flag(p.seq_ready + bb) == 0) __nanosleep(100);
+            wait_all_seq_ready(p);
             __threadfence();
             __syncthreads();
         }
@@ -165,7 +208,11 @@ SD_DEVINL void kv_col_body(const KvParams& p, const int cta_x, const int layer) 
                 asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(p.seq_ready + b) : "memory");
             }
 #else
-            while (ld_flag(p.seq_ready + b) == 0) __nanosleep(100);
+            SpinGuard guard;
+            while (ld_flag(p.seq_ready + b) == 0) {
+                if (!guard.keep_waiting(kSpinSeqFlag)) break;
+                __nanosleep(100);
+            }
             __threadfence();
 #endif
         }
@@ -214,8 +261,7 @@ SD_DEVINL void kv_col_body(const KvParams& p, const int cta_x, const int layer) 
             // epoch, so every local finalizer must have read it first -- it raises its flag after the push.
             // lag = 0 implies this (the gather waits for the rank's own records); lag = 1 does not: without
             // this wait a late finalizer tags its record with the NEXT epoch and the step after hangs.
-            for (int bb = threadIdx.x; bb < p.B; bb += blockDim.x)
-                while (ld_flag(p.seq_ready + bb) == 0) __nanosleep(100);
+            wait_all_seq_ready(p);
             __syncthreads();
         }
 #endif
@@ -225,123 +271,287 @@ SD_DEVINL void kv_col_body(const KvParams& p, const int cta_x, const int layer) 
 }
 
 
-// ---- "copy-all" append for the fused step (mode 2 of sd_verify_append) -------------------------------
-// The append CTAs copy ALL R offered rows of their sequences and therefore depend on nothing the verify
-// part produces: they never wait, so they can sit in front of their group's verify CTAs in block order
-// and stream concurrently.  What does depend on accept_len -- zeroing the rejected slots and advancing
-// the length -- is done by the verify finalizer of the sequence, after the copy CTAs of its group have
-// signalled completion (group counter).
-struct FusedAppend {
-    int enabled;
-    const sd_kv_layer* layers;
-    int n_layers, H, R, spc;  // spc = sequences per group (per append x-slot)
-    int64_t row_bytes, capacity, arena_stride_b, arena_stride_h;
-    int32_t* seq_lens;
-    int32_t* overflow;
-    unsigned* group_cnt;      // [2 * groups]: {copy CTAs done, finalizers done}; all zero between launches
-    int zero_rejected;
+// ---- lagged append: the accept_len-dependent row moves, spread UNDER the verify phase ----------------
+// (fused step, verify_step_kernel in sd_verify.cu).  The append of one sequence -- n_layers * H * R rows of K and
+// of V -- is cut into `pieces` equal runs of items (item = the K and the V vector of one 16-byte column of one
+// row: one index decode, by multiply-shift, serves both), one run per verify CTA of a sequence, and
+// the pieces of sequence b are carried by the verify CTAs of sequence b + lag: by the time those run, b's
+// finalizer has (almost always) published its word, so they fetch exactly the kept rows while their own logits
+// chunk is in flight and store them once their partial is published.  Every arena byte is written exactly
+// once (kept row or zero), by a CTA that knows accept_len: no copy-then-zero pass, no fence on the data path.
+// The pieces of the last `lag` sequences are carried by tail CTAs behind the verify CTAs; their rows are pulled
+// into L2 early by those sequences' own verify CTAs (kv_piece_prefetch).
+//
+// Sequence word (one 8-byte volatile store by the finalizer, polled by the consumers):
+//   bits 63..40  tag = (launch epoch + 1) & 0xffffff   -- words of earlier launches never match: no re-arming
+//   bits 39..32  n_keep = accept_len + 1 (1..65)
+//   bits 31..0   the sequence's length BEFORE this step
+// The finalizer is the only reader and the only writer of seq_lens[b] in the launch (it stores the new length
+// right away), so lengths need no ticket, and a consumer gets everything it needs from ONE load.
+SD_DEVINL unsigned long long ld_word64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+SD_DEVINL unsigned step_tag(const unsigned* epoch_word) {
+    unsigned e;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(e) : "l"(epoch_word) : "memory");
+    return (e + 1u) & 0xffffffu;
+}
+SD_DEVINL bool word_valid(unsigned long long w, unsigned tag) {
+    return (unsigned)(w >> 40) == tag && ((unsigned)(w >> 32) & 0xffu) != 0u;
+}
+SD_DEVINL unsigned long long make_word(unsigned tag, int n_keep, int len) {
+    return ((unsigned long long)tag << 40) | ((unsigned long long)(unsigned)(n_keep & 0xff) << 32) | (unsigned)len;
+}
+
+// item of a sequence's append -> offsets.  ONE decode serves two vectors (K and V share everything but the base).
+struct PieceItem {
+    int64_t src_off, dst_off;  // dst_off excludes the length term (+ len * row_bytes)
+    int j, layer;
+};
+SD_DEVINL PieceItem piece_item(const KvParams& p, const int seq, const int it) {
+    int t = fd_div(p.fd_vpr, it);
+    const int v = it - t * (int)p.fd_vpr.d;
+    int t2 = fd_div(p.fd_R, t);
+    PieceItem r;
+    r.j = t - t2 * (int)p.fd_R.d;
+    r.layer = fd_div(p.fd_H, t2);
+    const int h = t2 - r.layer * (int)p.fd_H.d;
+    r.src_off = (int64_t)seq * p.new_stride_b + (int64_t)h * p.new_stride_h + (int64_t)r.j * p.new_stride_r + ((int64_t)v << 4);
+    r.dst_off = (int64_t)seq * p.arena_stride_b + (int64_t)h * p.arena_stride_h + (int64_t)r.j * p.row_bytes + ((int64_t)v << 4);
+    return r;
+}
+struct PtrPair {
+    const char* k;
+    const char* v;
+};
+SD_DEVINL PtrPair unpack_pair(const uint4& q) {
+    PtrPair r;
+    r.k = reinterpret_cast<const char*>(((unsigned long long)q.y << 32) | q.x);
+    r.v = reinterpret_cast<const char*>(((unsigned long long)q.w << 32) | q.z);
+    return r;
+}
+SD_DEVINL PtrPair layer_src(const KvParams& p, const int layer) {  // {new_k, new_v} of a layer
+    if (p.uniform) {
+        const int64_t o = (int64_t)layer * p.ls_new;
+        return PtrPair{reinterpret_cast<const char*>(p.layer0.new_k) + o, reinterpret_cast<const char*>(p.layer0.new_v) + o};
+    }
+    return unpack_pair(__ldg(reinterpret_cast<const uint4*>(&p.layers[layer].new_k)));
+}
+SD_DEVINL PtrPair layer_dst(const KvParams& p, const int layer) {  // {arena_k, arena_v}
+    if (p.uniform) {
+        const int64_t o = (int64_t)layer * p.ls_arena;
+        return PtrPair{reinterpret_cast<const char*>(p.layer0.arena_k) + o, reinterpret_cast<const char*>(p.layer0.arena_v) + o};
+    }
+    return unpack_pair(__ldg(reinterpret_cast<const uint4*>(&p.layers[layer].arena_k)));
+}
+
+// The fetched rows are PARKED in shared memory (cp.async, 16 bytes per request, L2-only): no data registers are
+// held across the CTA's own reduction, and every request is in flight from the first microsecond of the CTA.
+// park layout: uint4 park[2 * NI][blockDim.x] -- slot (2u + kv) of thread t at park[(2u + kv) * blockDim.x + t].
+constexpr int kCarryNI = 2;  // items a carrying verify CTA parks per thread (16 KB of shared memory at 256 threads)
+
+SD_DEVINL void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+SD_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+struct PieceRegs {
+    unsigned long long word;       // last observed sequence word
+    int64_t dst_off[kCarryNI];
+    int jl[kCarryNI];              // row | layer << 8 of parked item u (-1: none)
+    int seq, it, it_end;           // this thread owns items it, it + blockDim.x, ... < it_end of the sequence's append
 };
 
-template <int RB>
-SD_DEVINL void kv_copy_all_body(const KvParams& p, const int cta_x, const int layer, unsigned* group_cnt) {
-    const int vpr = (int)(p.row_bytes >> 4);
-    const int64_t slots = (int64_t)p.B * p.H * vpr;
-    const int64_t slot = (int64_t)cta_x * blockDim.x + threadIdx.x;
-    if (slot < slots) {
-        const int v = (int)(slot % vpr);
-        const int64_t t = slot / vpr;
-        const int h = (int)(t % p.H);
-        const int b = (int)(t / p.H);
-        const sd_kv_layer L = p.layers[layer];
-        const int len = p.seq_lens ? p.seq_lens[b] : 0;  // the finalizer advances it only after this CTA has signalled
-        int room = (int)(p.capacity - len);
-        room = room < 0 ? 0 : (room > p.R ? p.R : room);
-        const char* sk = reinterpret_cast<const char*>(L.new_k) + (int64_t)b * p.new_stride_b + (int64_t)h * p.new_stride_h + ((int64_t)v << 4);
-        const char* sv = reinterpret_cast<const char*>(L.new_v) + (int64_t)b * p.new_stride_b + (int64_t)h * p.new_stride_h + ((int64_t)v << 4);
-        const int64_t doff = (int64_t)b * p.arena_stride_b + (int64_t)h * p.arena_stride_h + (int64_t)len * p.row_bytes + ((int64_t)v << 4);
-        char* dk = reinterpret_cast<char*>(L.arena_k) + doff;
-        char* dv = reinterpret_cast<char*>(L.arena_v) + doff;
-        for (int j0 = 0; j0 < room; j0 += RB) {
-            uint4 kx[RB], vx[RB];
+// Phase 1 (before the CTA's own work): look at the sequence word; if it is already published fetch only kept
+// rows, else fetch regardless (the rows are inputs of the launch, so this never waits).
+SD_DEVINL void kv_piece_begin(const KvParams& p, const int seq, const int piece, const unsigned tag, PieceRegs& r, uint4* park) {
+    r.seq = seq;
+    const int base = piece * p.piece_items;
+    r.it_end = base + p.piece_items < p.seq_items ? base + p.piece_items : p.seq_items;
+    r.it = base + (int)threadIdx.x;
+    r.word = ld_word64(p.flags + seq);
+    const int n = (!p.eager_rows && word_valid(r.word, tag)) ? (int)((unsigned)(r.word >> 32) & 0xffu) : p.R;
 #pragma unroll
-            for (int u = 0; u < RB; ++u) {
-                const int j = j0 + u;
-                if (j < room) {
-                    kx[u] = ldg_stream_v4(sk + (int64_t)j * p.new_stride_r);
-                    vx[u] = ldg_stream_v4(sv + (int64_t)j * p.new_stride_r);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < RB; ++u) {
-                const int j = j0 + u;
-                if (j < room) {
-                    *reinterpret_cast<uint4*>(dk + (int64_t)j * p.row_bytes) = kx[u];
-                    *reinterpret_cast<uint4*>(dv + (int64_t)j * p.row_bytes) = vx[u];
-                }
+    for (int u = 0; u < kCarryNI; ++u) {
+        const int it = r.it + u * (int)blockDim.x;
+        r.jl[u] = -1;
+        if (u < p.carry_ni && it < r.it_end) {
+            const PieceItem pi = piece_item(p, seq, it);
+            const PtrPair src = layer_src(p, pi.layer);
+            r.dst_off[u] = pi.dst_off;
+            r.jl[u] = pi.j | (pi.layer << 8);
+            if (pi.j < n) {
+                cp_async16(park + (2 * u) * blockDim.x + threadIdx.x, src.k + pi.src_off);
+                cp_async16(park + (2 * u + 1) * blockDim.x + threadIdx.x, src.v + pi.src_off);
             }
         }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();  // the rows are visible before the finalizer (which may zero some of them) sees the count
-        atomicAdd(group_cnt + 2 * cta_x, 1u);
     }
 }
 
-// The accept_len-dependent part of the append for sequence b, run by the verify finalizer CTA (all `nthreads`
-// threads): wait for the copy CTAs of b's group, zero the rejected slots, advance the length.
-SD_DEVINL void fused_append_finalize(const FusedAppend& fa, const int b, const int n_keep, const int tid, const int nthreads,
-                                     const bool named_barrier) {
-    const int g = b / fa.spc;
-    if (tid == 0) {
-        unsigned v;
-        for (;;) {
-            asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(fa.group_cnt + 2 * g) : "memory");
-            if (v >= (unsigned)fa.n_layers) break;
-            __nanosleep(64);
-        }
-        __threadfence();
+struct PieceKeep {
+    int len, n, nstore;
+};
+// wait (bounded) for the sequence word; false = it never came (no stores)
+SD_DEVINL bool piece_wait(const KvParams& p, const unsigned tag, const int seq, unsigned long long& word, PieceKeep& k) {
+    SpinGuard guard;
+    while (!word_valid(word, tag)) {
+        if (!guard.keep_waiting(kSpinSeqFlag)) return false;
+        __nanosleep(64);
+        word = ld_word64(p.flags + seq);
     }
-    if (named_barrier) asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-    else __syncthreads();
-    const int len = fa.seq_lens[b];
-    int room = (int)(fa.capacity - len);
-    room = room < 0 ? 0 : (room > fa.R ? fa.R : room);
-    int n = n_keep < 0 ? 0 : (n_keep > fa.R ? fa.R : n_keep);
-    if (n > room) {
-        if (fa.overflow && tid == 0) *fa.overflow = 1;
-        n = room;
-    }
-    if (fa.zero_rejected && room > n) {
-        const int vpr = (int)(fa.row_bytes >> 4);
-        const int rej = room - n;
-        const int64_t items = (int64_t)fa.n_layers * 2 * fa.H * rej * vpr;
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        for (int64_t i = tid; i < items; i += nthreads) {
-            const int v = (int)(i % vpr);
-            int64_t t = i / vpr;
-            const int j = (int)(t % rej);
-            t /= rej;
-            const int h = (int)(t % fa.H);
-            t /= fa.H;
-            const int kv = (int)(t & 1);
-            const int layer = (int)(t >> 1);
-            const sd_kv_layer L = fa.layers[layer];
-            char* dst = reinterpret_cast<char*>(kv ? L.arena_v : L.arena_k) + (int64_t)b * fa.arena_stride_b +
-                        (int64_t)h * fa.arena_stride_h + (int64_t)(len + n + j) * fa.row_bytes + ((int64_t)v << 4);
-            *reinterpret_cast<uint4*>(dst) = z;
+    k.len = (int)(unsigned)word;
+    int n = (int)((unsigned)(word >> 32) & 0xffu);
+    const int64_t room64 = p.capacity - k.len;
+    const int room = room64 < 0 ? 0 : (room64 > p.R ? p.R : (int)room64);
+    k.n = n > room ? room : n;
+    k.nstore = p.zero_rejected ? room : k.n;
+    return true;
+}
+
+// items it0, it0 + blockDim.x, ... < it_end, `ni` per thread and pass parked in shared memory: all requests of a
+// pass first (every offered row while the word is unknown), then the stores.  Used by the tail CTAs (ni = what the
+// CTA's shared memory holds) and for pieces longer than kCarryNI items per thread.
+SD_DEVINL void piece_items_run(const KvParams& p, const unsigned tag, const int seq, int it0, const int it_end,
+                               unsigned long long& word, uint4* park, const int ni) {
+    PieceKeep keep{0, 0, 0};
+    bool known = word_valid(word, tag);
+    if (known && !piece_wait(p, tag, seq, word, keep)) return;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (; it0 < it_end; it0 += ni * (int)blockDim.x) {
+        for (int u = 0; u < ni; ++u) {
+            const int it = it0 + u * (int)blockDim.x;
+            if (it >= it_end) break;
+            const PieceItem pi = piece_item(p, seq, it);
+            if (!known || pi.j < keep.n) {
+                const PtrPair src = layer_src(p, pi.layer);
+                cp_async16(park + (2 * u) * blockDim.x + threadIdx.x, src.k + pi.src_off);
+                cp_async16(park + (2 * u + 1) * blockDim.x + threadIdx.x, src.v + pi.src_off);
+            }
+        }
+        if (!known) {
+            if (!piece_wait(p, tag, seq, word, keep)) {
+                cp_async_wait_all();
+                return;
+            }
+            known = true;
+        }
+        cp_async_wait_all();
+        const int64_t len_off = (int64_t)keep.len * p.row_bytes;
+        for (int u = 0; u < ni; ++u) {
+            const int it = it0 + u * (int)blockDim.x;
+            if (it >= it_end) break;
+            const PieceItem pi = piece_item(p, seq, it);
+            if (pi.j < keep.nstore) {
+                const PtrPair dst = layer_dst(p, pi.layer);
+                const bool kept = pi.j < keep.n;
+                *reinterpret_cast<uint4*>(const_cast<char*>(dst.k) + pi.dst_off + len_off) =
+                    kept ? park[(2 * u) * blockDim.x + threadIdx.x] : z;
+                *reinterpret_cast<uint4*>(const_cast<char*>(dst.v) + pi.dst_off + len_off) =
+                    kept ? park[(2 * u + 1) * blockDim.x + threadIdx.x] : z;
+            }
         }
     }
-    if (named_barrier) asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-    else __syncthreads();
-    if (tid == 0) {
-        fa.seq_lens[b] = len + n;
-        // the last finalizer of the group re-arms its counters for the next launch
-        const unsigned done = atomicAdd(fa.group_cnt + 2 * g + 1, 1u);
-        if (done + 1u == (unsigned)fa.spc) {
-            fa.group_cnt[2 * g] = 0u;
-            fa.group_cnt[2 * g + 1] = 0u;
+}
+
+// Phase 2 (after the CTA has published its own result): wait for the word if needed, store kept rows and zeros.
+SD_DEVINL void kv_piece_finish(const KvParams& p, const unsigned tag, PieceRegs& r, uint4* park) {
+    PieceKeep keep;
+    const bool ok = piece_wait(p, tag, r.seq, r.word, keep);
+    cp_async_wait_all();  // (also on the failure path: no request may outlive the CTA's shared memory)
+    if (!ok) return;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    const int64_t len_off = (int64_t)keep.len * p.row_bytes;
+#pragma unroll
+    for (int u = 0; u < kCarryNI; ++u) {
+        if (r.jl[u] < 0) continue;
+        const int j = r.jl[u] & 0xff;
+        if (j < keep.nstore) {
+            const PtrPair dst = layer_dst(p, r.jl[u] >> 8);
+            const bool kept = j < keep.n;
+            *reinterpret_cast<uint4*>(const_cast<char*>(dst.k) + r.dst_off[u] + len_off) =
+                kept ? park[(2 * u) * blockDim.x + threadIdx.x] : z;
+            *reinterpret_cast<uint4*>(const_cast<char*>(dst.v) + r.dst_off[u] + len_off) =
+                kept ? park[(2 * u + 1) * blockDim.x + threadIdx.x] : z;
         }
+    }
+    // pieces longer than carry_ni items per thread (small vocabularies: few verify CTAs per sequence)
+    if (r.it + p.carry_ni * (int)blockDim.x < r.it_end)
+        piece_items_run(p, tag, r.seq, r.it + p.carry_ni * (int)blockDim.x, r.it_end, r.word, park, p.carry_ni);
+}
+
+// whole CTA: wait until every sequence word of this launch is published (bounded)
+SD_DEVINL void wait_all_words(const KvParams& p, const unsigned tag) {
+    for (int bb = threadIdx.x; bb < p.B; bb += blockDim.x) {
+        SpinGuard guard;
+        while (!word_valid(ld_word64(p.flags + bb), tag)) {
+            if (!guard.keep_waiting(kSpinAllFlags)) break;
+            __nanosleep(100);
+        }
+    }
+}
+
+// Verify CTAs of the last `lag` sequences: nobody behind them carries their rows -- tail CTAs do, after the verify
+// CTAs.  A tail CTA is dispatched late, when the memory system is still queueing ~20 MB of bulk copies (a DRAM
+// round trip then takes ~3.5 us), so the rows it will want are pulled into L2 HERE, early and fire-and-forget
+// (no register, no shared memory, no wait): the tail's fetches become L2 hits.
+SD_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+SD_DEVINL void kv_piece_prefetch(const KvParams& p, const int seq, const int piece) {
+    const int base = piece * p.piece_items;
+    const int it_end = base + p.piece_items < p.seq_items ? base + p.piece_items : p.seq_items;
+    // one request per 128-byte line: 8 consecutive items (16-byte columns of one row) share a line
+    for (int it = base + 8 * (int)threadIdx.x; it < it_end; it += 8 * (int)blockDim.x) {
+        const PieceItem pi = piece_item(p, seq, it);
+        const PtrPair src = layer_src(p, pi.layer);
+        prefetch_l2(src.k + pi.src_off);
+        prefetch_l2(src.v + pi.src_off);
+    }
+}
+
+// Tail CTA t of the fused step: tail piece (t % tail_pieces) of sequence B - 1 - t / tail_pieces -- the LAST sequence
+// first: its CTAs are dispatched (and have their rows parked) before its word can possibly be there, while the
+// CTAs dispatched last serve the sequences whose words have long been published and never wait.  `park_items`
+// items per thread parked in the CTA's whole shared memory, every offered row requested by the first instructions of
+// the CTA (no dependence on the word).  The last tail CTA to retire closes the launch: once every sequence word is
+// published -- i.e. every verify CTA has published its partial, before which it has consumed the epoch -- it serves
+// the multi-GPU exchange and advances the launch epoch.
+SD_DEVINL void kv_tail_body(const KvParams& p, const int t, unsigned long long* trace, uint4* park, const int park_items) {
+    const int seq = p.B - 1 - t / p.tail_pieces, tp = t % p.tail_pieces;
+    const unsigned tag = step_tag(p.epoch_word);
+    {
+        const int tail_items = (p.seq_items + p.tail_pieces - 1) / p.tail_pieces;
+        const int it0 = tp * tail_items;
+        const int it_end = it0 + tail_items < p.seq_items ? it0 + tail_items : p.seq_items;
+        unsigned long long word = 0ull;  // "unknown": request every offered row now, look at the word afterwards
+        piece_items_run(p, tag, seq, it0 + (int)threadIdx.x, it_end, word, park, park_items);
+    }
+    if (trace && threadIdx.x == 0) trace[1] = global_timer_ns();
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(reinterpret_cast<unsigned*>(p.ticket), 1u);
+        s_last = prev == p.total_ctas - 1u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    wait_all_words(p, tag);
+    __syncthreads();
+    if (p.xchg) {
+        if (p.xchg_packed) {  // records pushed from here: the finalizers released them before publishing their words
+            __threadfence();
+            exchange_push_cta(p.xchg, p.xchg_packed, p.B);
+        }
+        // (the gather ends by advancing the exchange epoch, which every local finalizer has read: it publishes its
+        // word after its push)
+        exchange_gather_cta(p.xchg, p.xchg_out);
+    }
+    if (threadIdx.x == 0) {
+        unsigned e;
+        asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(e) : "l"(p.epoch_word) : "memory");
+        *reinterpret_cast<volatile unsigned*>(p.epoch_word) = (e + 1u == 0xffffffffu) ? 0u : e + 1u;
+        *p.ticket = 0;
     }
 }
 

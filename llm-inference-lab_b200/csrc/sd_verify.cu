@@ -77,7 +77,15 @@ struct VerifyParams {
     float inv_temperature;
     const sd_exchange* xchg;    // nullable: peer-memory result exchange (device memory)
     int32_t* seq_ready;         // nullable: flag b is raised once sequence b's outputs are final
-    FusedAppend fa;             // copy-all fused step: the finalizer zeroes the rejected KV slots and advances the length
+    // lagged fused step (verify_step_kernel): the finalizer publishes the sequence word {tag, n_keep, old length}
+    // and stores the new length; all null / zero otherwise (sd_kv_col.cuh)
+    unsigned long long* words;
+    unsigned* epoch_word;
+    int32_t* seq_lens;
+    int32_t* kv_overflow;
+    int64_t kv_capacity;
+    int kv_R;
+    int word_release;           // 1 = a CTA reads the packed records after seeing the words (push from the append part)
     unsigned long long* trace;  // evidence runs: [grid][4] = {globaltimer at entry, after the scan, at exit, smid}
 };
 
@@ -379,7 +387,8 @@ SD_DEVINL bool publish_segment(const VerifyParams& p, const RowGeom<T>& g, Threa
 // write the outputs and re-arm the slots.  `nslots` = partial slots in use per row for tiled launches,
 // 0 = derive them from the persistent partition.  Called by all `nthreads` reducing threads.
 template <typename T, bool STATS, bool NAMED>
-SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int nslots, const int tid, const int nthreads) {
+SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int nslots, const int tid, const int nthreads,
+                                 const unsigned tag = 0u) {
     const int V = p.V;
     const int lane = tid & 31, wid = tid >> 5, nwarps = nthreads >> 5;
     __shared__ int s_tgt[64];
@@ -404,10 +413,12 @@ SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int n
         // ns <= kMaxChunks = 64: two slots per lane.  Their producers were dispatched before this CTA
         // (lower block index) and wait on nothing, so the poll terminates.
         unsigned long long v0 = 1ull, v1 = 1ull;
+        SpinGuard guard;  // (all lanes poll the same number of times: the verdict is warp-uniform)
         for (;;) {
             if (lane < ns) v0 = ld_volatile_u64(slots + 2 * lane);
             if (lane + 32 < ns) v1 = ld_volatile_u64(slots + 2 * (lane + 32));
             if (__all_sync(0xffffffffu, v0 != 0ull && v1 != 0ull)) break;
+            if (!__all_sync(0xffffffffu, guard.keep_waiting(kSpinPartials))) break;
             __nanosleep(40);
         }
         Cand best{0u, 0x7fffffff};
@@ -510,11 +521,25 @@ SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int n
             }
         }
     }
-    if (p.fa.enabled) {
-        __shared__ int s_nacc;
-        if (tid == 0) s_nacc = p.accept_len[b];  // written by this thread a few lines above
-        cta_sync<NAMED>(nthreads);
-        fused_append_finalize(p.fa, b, s_nacc + 1, tid, nthreads, NAMED);
+    if (wid == 0 && p.words) {
+        // lagged fused step: publish {tag, n_keep, old length} in ONE 8-byte store and advance the length (this
+        // thread is the only reader and writer of seq_lens[b] in the launch).  After the peer push above, so a
+        // CTA that has seen every word knows every finalizer has read the exchange epoch.
+        __syncwarp();
+        if (lane == 0) {
+            const int len = p.seq_lens ? p.seq_lens[b] : 0;
+            const int n_keep = p.accept_len[b] + 1;  // written by this thread a few lines above
+            int64_t room = p.kv_capacity - len;
+            room = room < 0 ? 0 : (room > p.kv_R ? p.kv_R : room);
+            int n = n_keep > p.kv_R ? p.kv_R : n_keep;
+            if (n > room) {
+                if (p.kv_overflow) *p.kv_overflow = 1;
+                n = (int)room;
+            }
+            if (p.seq_lens) p.seq_lens[b] = len + n;
+            if (p.word_release) __threadfence();
+            st_volatile_u64(p.words + b, make_word(tag, n_keep > p.kv_R ? p.kv_R : n_keep, len));
+        }
     }
     if (wid == 0 && p.seq_ready) {
         // per-sequence completion flag: lets the kv_append launch that follows start on sequence b while other
@@ -804,14 +829,69 @@ __global__ void __launch_bounds__(256) verify_bulk_kernel(const VerifyParams p) 
 }
 
 // ---- the whole step in ONE launch: fused verify + kv_append ------------------------------------------
-// CTAs [0, n_verify) run the bulk-chunk verify body; CTAs [n_verify, n_verify + kv_gx * layers) run the
-// kv_append column body for (x, layer), each thread waiting for its sequence's completion flag (raised
-// by the verify finalizer, sd_kv_col.cuh).  Blocks are dispatched in index order, so append CTAs become
-// resident only when every verify CTA has started; they wait on flags, verify CTAs wait on nothing that
-// an append CTA produces -> no deadlock.  One launch overhead, one ramp and one tail per step instead of two.
-template <typename T, int RB>
-__global__ void __launch_bounds__(256, 4) verify_append_kernel(const VerifyParams vp, const KvParams kp, const int n_verify,
-                                                            const int kv_gx, const int interleave_group) {
+// Default ("lagged append", verify_step_kernel): CTAs [0, n_verify) each reduce one logits chunk AND carry one
+// piece of the append of the sequence `lag` places earlier (sd_kv_col.cuh): the piece's rows are requested right
+// after the chunk's bulk copy, so both are in flight together, and stored after the CTA's partial is published.
+// The append traffic therefore streams UNDER the verify phase instead of after it, and nothing on the verify
+// critical path waits for an append.  CTAs [n_verify, n_verify + lag * pieces) are the tail: the pieces of the
+// last `lag` sequences, the multi-GPU gather and the epoch advance.
+// Progress: a CTA only ever waits for words / partials produced by CTAs with a LOWER block index (the finalizer of
+// an earlier sequence; the chunks of its own sequence), which wait, transitively, only on still lower ones.
+// REQUIREMENT (stated in include/sd_verify.h): the hardware dispatches the blocks of a 1-D grid in index order, so
+// every CTA a resident CTA waits for is resident or finished.  Every wait is bounded (SpinGuard).
+template <typename T>
+SD_DEVINL void step_cta_body(const VerifyParams& p, const KvParams& kp, const int unit, unsigned char* stage, uint64_t* bar,
+                             uint4* park) {
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int chunk = unit % p.S;
+    const int row = unit / p.S;
+    const int b = row / p.rows;
+    const int it0 = chunk * p.units_per_chunk;
+    int it1 = it0 + p.units_per_chunk;
+    if (it1 > p.upr) it1 = p.upr;
+    const RowGeom<T> g = row_geom<T>(p, row);
+    const int v0 = it0 * nthreads;
+    int nv = g.nvec - v0;
+    const int cap = (it1 - it0) * nthreads;
+    nv = nv < 0 ? 0 : (nv > cap ? cap : nv);
+    if (tid == 0) {
+        if (kp.stagger_ns > 0 && unit < 4 * 148) __nanosleep((unsigned)((unit / 148) * kp.stagger_ns));  // A/B: de-synchronise the first wave
+        if (nv > 0) {
+            vbar_arrive_expect_tx(bar, (unsigned)nv * 16u);
+            vbulk_g2s(stage, g.vp + v0, (unsigned)nv * 16u, bar);
+        } else {
+            vbar_arrive(bar);
+        }
+    }
+    // The launch epoch is CONSUMED here (the branch cannot be resolved before the load returns), i.e. before this
+    // CTA publishes anything: the closing CTA advances the epoch only after every partial has been published.
+    unsigned epoch_raw;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(epoch_raw) : "l"(kp.epoch_word) : "memory");
+    if (epoch_raw == 0xffffffffu) return;  // (never a valid epoch: the closing CTA skips it)
+    const unsigned tag = (epoch_raw + 1u) & 0xffffffu;
+    const int lag = kp.lag;
+    const int piece = unit - b * kp.pieces;
+    const bool carries = b >= lag;
+    PieceRegs pr;
+    if (carries) kv_piece_begin(kp, b - lag, piece, tag, pr, park);
+    if (b >= p.B - lag && kp.l2_prefetch) kv_piece_prefetch(kp, b, piece);  // rows of a tail sequence: into L2, now
+    ThreadAcc<T, false> acc;
+    acc.reset();
+    vbar_wait(bar, 0u);
+    const uint4* src = reinterpret_cast<const uint4*>(stage);
+#pragma unroll 4
+    for (int k = tid; k < nv; k += nthreads) acc.add(src[k], v0 + k, true, p.scale_log2);
+    if (p.trace && tid == 0) p.trace[(size_t)blockIdx.x * 4 + 1] = global_timer_ns();
+    if (publish_segment<T, false, false>(p, g, acc, row, it0, it1, chunk, tid, nthreads))
+        finalize_sequence<T, false, false>(p, b, p.S, tid, nthreads, tag);
+    if (carries) kv_piece_finish(kp, tag, pr, park);
+}
+
+// dynamic shared memory: [stage_bytes: the logits chunk][park: kCarryNI * 2 * 16 * blockDim.x bytes of parked KV rows];
+// a tail CTA parks rows in all of it (tail_park_items per thread, one pass)
+template <typename T>
+__global__ void __launch_bounds__(256, 4) verify_step_kernel(const VerifyParams vp, const KvParams kp, const int n_verify,
+                                                          const int stage_bytes, const int tail_park_items) {
     extern __shared__ __align__(128) unsigned char stage[];
     __shared__ __align__(8) uint64_t bar;
     if (threadIdx.x == 0) {
@@ -821,25 +901,36 @@ __global__ void __launch_bounds__(256, 4) verify_append_kernel(const VerifyParam
     __syncthreads();
     pdl_wait();
     pdl_trigger();
-    if (vp.fa.enabled) {
-        // copy-all mode: group = [append CTAs of the group's sequences: one per layer, copying all R rows, waiting
-        // on nothing][the group's verify CTAs, whose finalizers zero the rejected slots and advance the lengths]
-        const int g = (int)blockIdx.x / interleave_group, r = (int)blockIdx.x - g * interleave_group;
-        if (r < kp.n_layers) kv_copy_all_body<RB>(kp, g, r, vp.fa.group_cnt);
-        else verify_bulk_body<T, false>(vp, g * (interleave_group - kp.n_layers) + (r - kp.n_layers), stage, &bar);
-        return;
+    if (vp.trace && threadIdx.x == 0) {  // evidence runs (tools/trace_step.py): {entry, scan done / rows stored, exit, SM id}
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        vp.trace[(size_t)blockIdx.x * 4 + 0] = global_timer_ns();
+        vp.trace[(size_t)blockIdx.x * 4 + 3] = smid;
     }
-    if (interleave_group > 0) {
-        // Interleaved order: the append CTAs of a group of sequences come right after that group's verify CTAs,
-        // so they are dispatched in the middle of the grid, wait about one CTA lifetime for their flags and
-        // move their rows while later sequences are still being verified (no serialised append phase).
-        // group = verify_per_group verify CTAs + kp.n_layers append CTAs (one kv x-slot, every layer).
-        const int g = (int)blockIdx.x / interleave_group, r = (int)blockIdx.x - g * interleave_group;
-        const int verify_per_group = interleave_group - kp.n_layers;
-        if (r < verify_per_group) verify_bulk_body<T, false>(vp, g * verify_per_group + r, stage, &bar);
-        else kv_col_body<RB>(kp, g, r - verify_per_group);
-        return;
+    if ((int)blockIdx.x < n_verify)
+        step_cta_body<T>(vp, kp, (int)blockIdx.x, stage, &bar, reinterpret_cast<uint4*>(stage + stage_bytes));
+    else
+        kv_tail_body(kp, (int)blockIdx.x - n_verify, vp.trace ? vp.trace + (size_t)blockIdx.x * 4 : nullptr,
+                     reinterpret_cast<uint4*>(stage), tail_park_items);
+    if (vp.trace && threadIdx.x == 0) vp.trace[(size_t)blockIdx.x * 4 + 2] = global_timer_ns();
+}
+
+// Round-1 layout, kept for A/B evidence (sd_verify_append_set_mode(1, 0)): CTAs [0, n_verify) run the bulk-chunk
+// verify body, CTAs after them the kv_append column body for (x, layer), each thread waiting for its sequence's
+// completion flag.  The append CTAs become resident only when every verify CTA has started, so the two phases
+// serialise (measured: 34.6 us = 18.9 + 14.9).
+template <typename T, int RB>
+__global__ void __launch_bounds__(256, 4) verify_append_kernel(const VerifyParams vp, const KvParams kp, const int n_verify,
+                                                            const int kv_gx) {
+    extern __shared__ __align__(128) unsigned char stage[];
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+        vbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
+    pdl_wait();
+    pdl_trigger();
     if ((int)blockIdx.x < n_verify) {
         verify_bulk_body<T, false>(vp, (int)blockIdx.x, stage, &bar);
     } else {
@@ -916,23 +1007,15 @@ static cudaError_t launch_bulk_t(const VerifyParams& p, unsigned grid, int threa
     return launch_kernel(verify_bulk_kernel<T, STATS>, dim3(grid), dim3(threads), smem, st, p);
 }
 
-static int g_fused_copy_all = 0;    // 1 = copy-all fused step (needs a group-counter workspace, see sd_verify_append)
-static int g_fused_interleave = 0;  // evidence runs: 1 = append CTAs of a sequence group right after its verify CTAs (measured slower: 43 vs 34 us)
+static int g_fused_mode = 0;   // 0 = lagged append (default), 1 = round-1 layout (append CTAs behind all verify CTAs)
+static int g_fused_lag = 0;    // sequences of lag for mode 0 (0 = heuristic)
 
 template <typename T, int RB>
 static cudaError_t launch_fused_t(const VerifyParams& p, const KvParams& kp, unsigned total, int n_verify, int kv_gx,
                                   int threads, size_t smem, cudaStream_t st) {
-    // interleaving needs whole sequences per append x-slot and whole groups: n_verify = kv_gx * verify_per_group
-    int group = 0;
-    if ((g_fused_interleave || p.fa.enabled) && kv_gx > 0 && n_verify % kv_gx == 0) {
-        const long long threads_per_seq = (long long)kp.H * (kp.row_bytes / 16);
-        if (threads_per_seq > 0 && 256 % threads_per_seq == 0 && ((long long)kp.B * threads_per_seq) % 256 == 0)
-            group = n_verify / kv_gx + kp.n_layers;
-    }
-    if (p.fa.enabled && group == 0) return cudaErrorInvalidConfiguration;  // checked by the caller; never launch half a protocol
     cudaError_t e = cudaFuncSetAttribute(verify_append_kernel<T, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return launch_kernel(verify_append_kernel<T, RB>, dim3(total), dim3(threads), smem, st, p, kp, n_verify, kv_gx, group);
+    return launch_kernel(verify_append_kernel<T, RB>, dim3(total), dim3(threads), smem, st, p, kp, n_verify, kv_gx);
 }
 
 template <typename T>
@@ -941,10 +1024,7 @@ static cudaError_t launch_fused_rb(const VerifyParams& p, const KvParams& kp, in
     switch (rb) {
         case 1: return launch_fused_t<T, 1>(p, kp, total, n_verify, kv_gx, threads, smem, st);
         case 2: return launch_fused_t<T, 2>(p, kp, total, n_verify, kv_gx, threads, smem, st);
-        case 3: return launch_fused_t<T, 3>(p, kp, total, n_verify, kv_gx, threads, smem, st);
-        case 4: return launch_fused_t<T, 4>(p, kp, total, n_verify, kv_gx, threads, smem, st);
-        case 5: return launch_fused_t<T, 5>(p, kp, total, n_verify, kv_gx, threads, smem, st);
-        default: return launch_fused_t<T, 6>(p, kp, total, n_verify, kv_gx, threads, smem, st);
+        default: return launch_fused_t<T, 3>(p, kp, total, n_verify, kv_gx, threads, smem, st);
     }
 }
 
@@ -953,6 +1033,48 @@ static cudaError_t launch_fused(const VerifyParams& p, const KvParams& kp, int l
     if (logit_dtype == SD_F32) return launch_fused_rb<float>(p, kp, rb, total, n_verify, kv_gx, threads, smem, st);
     if (logit_dtype == SD_F16) return launch_fused_rb<__half>(p, kp, rb, total, n_verify, kv_gx, threads, smem, st);
     return launch_fused_rb<__nv_bfloat16>(p, kp, rb, total, n_verify, kv_gx, threads, smem, st);
+}
+
+template <typename T>
+static cudaError_t launch_step_t(const VerifyParams& p, const KvParams& kp, unsigned total, int n_verify, int threads,
+                                 size_t stage_bytes, size_t smem, int tail_park_items, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(verify_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return launch_kernel(verify_step_kernel<T>, dim3(total), dim3(threads), smem, st, p, kp, n_verify, (int)stage_bytes,
+                         tail_park_items);
+}
+
+static cudaError_t launch_step(const VerifyParams& p, const KvParams& kp, int logit_dtype, unsigned total, int n_verify,
+                               int threads, size_t stage_bytes, size_t smem, int tail_park_items, cudaStream_t st) {
+    if (logit_dtype == SD_F32) return launch_step_t<float>(p, kp, total, n_verify, threads, stage_bytes, smem, tail_park_items, st);
+    if (logit_dtype == SD_F16) return launch_step_t<__half>(p, kp, total, n_verify, threads, stage_bytes, smem, tail_park_items, st);
+    return launch_step_t<__nv_bfloat16>(p, kp, total, n_verify, threads, stage_bytes, smem, tail_park_items, st);
+}
+
+// resident CTAs per SM of the fused step kernel (registers: 4; shared memory: chunk stage + parked rows)
+static int step_occupancy(int logit_dtype, int threads, size_t smem) {
+    static size_t cached_smem[3] = {0, 0, 0};
+    static int cached_n[3] = {0, 0, 0};
+    if (cached_n[logit_dtype] > 0 && cached_smem[logit_dtype] == smem) return cached_n[logit_dtype];
+    int n = 0;
+    cudaError_t e;
+    if (logit_dtype == SD_F32) {
+        cudaFuncSetAttribute(verify_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, verify_step_kernel<float>, threads, smem);
+    } else if (logit_dtype == SD_F16) {
+        cudaFuncSetAttribute(verify_step_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, verify_step_kernel<__half>, threads, smem);
+    } else {
+        cudaFuncSetAttribute(verify_step_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, verify_step_kernel<__nv_bfloat16>, threads, smem);
+    }
+    if (e != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        n = 4;
+    }
+    cached_smem[logit_dtype] = smem;
+    cached_n[logit_dtype] = n;
+    return n;
 }
 
 // resident CTAs per SM of the persistent kernel for (T, vpt, stats, threads); cached per combination
@@ -994,7 +1116,7 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
                       float* row_max, float* row_sumexp, void* workspace, size_t workspace_bytes, int B,
                       int rows, int K, int V, void* stream, const sd_exchange* exchange, int32_t* seq_ready,
                       const KvParams* fused_kv = nullptr, unsigned fused_gx = 0, int fused_rb = 0,
-                      unsigned* fused_group_cnt = nullptr) {
+                      int32_t* step_state = nullptr) {
     if (B < 0 || K < 0 || V <= 0 || rows <= 0) return SD_ERR_INVALID_ARG;
     if (rows != K && rows != K + 1) return SD_ERR_SHAPE;
     if (rows > 64) return SD_ERR_UNSUPPORTED;
@@ -1078,7 +1200,13 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
     p.trace = nullptr;
     p.xchg = exchange;
     p.seq_ready = seq_ready;
-    p.fa.enabled = 0;
+    p.words = nullptr;
+    p.epoch_word = nullptr;
+    p.seq_lens = nullptr;
+    p.kv_overflow = nullptr;
+    p.kv_capacity = 0;
+    p.kv_R = 0;
+    p.word_release = 0;
 
     unsigned grid;
     int tma_stages = 0;
@@ -1127,31 +1255,88 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
     cudaError_t e;
     if (fused_kv) {
         if (variant != 3 || stats) return SD_ERR_UNSUPPORTED;
-        if (fused_group_cnt) {
-            // copy-all mode: whole groups only (whole sequences per append x-slot, whole x-slots per batch)
-            const long long tps = (long long)fused_kv->H * (fused_kv->row_bytes / 16);
-            const bool whole = fused_gx > 0 && grid % fused_gx == 0 && tps > 0 && 256 % tps == 0 && ((long long)B * tps) % 256 == 0;
-            if (!whole || fused_kv->xchg) return SD_ERR_UNSUPPORTED;
-            p.fa.enabled = 1;
-            p.fa.layers = fused_kv->layers;
-            p.fa.n_layers = fused_kv->n_layers;
-            p.fa.H = fused_kv->H;
-            p.fa.R = fused_kv->R;
-            p.fa.spc = (int)(256 / tps);
-            p.fa.row_bytes = fused_kv->row_bytes;
-            p.fa.capacity = fused_kv->capacity;
-            p.fa.arena_stride_b = fused_kv->arena_stride_b;
-            p.fa.arena_stride_h = fused_kv->arena_stride_h;
-            p.fa.seq_lens = fused_kv->seq_lens_out;
-            p.fa.overflow = fused_kv->overflow;
-            p.fa.group_cnt = fused_group_cnt;
-            p.fa.zero_rejected = fused_kv->zero_rejected;
-            p.seq_ready = nullptr;
-        }
         const size_t smem = (size_t)p.units_per_chunk * threads * 16;
+        if (step_state) {
+            // lagged append (default): step_state = u64 words[B] | u32 epoch | u32 reserved
+            KvParams kp = *fused_kv;
+            kp.flags = reinterpret_cast<unsigned long long*>(step_state);
+            kp.epoch_word = reinterpret_cast<unsigned*>(step_state) + 2 * (size_t)B;
+            kp.seq_ready = nullptr;
+            kp.pieces = rows * p.S;
+            const long long seq_items = (long long)kp.n_layers * kp.H * kp.R * (kp.row_bytes / 16);
+            if (seq_items > 0x3fffffffLL || kp.R > 255 || kp.n_layers > (1 << 22)) return SD_ERR_UNSUPPORTED;
+            kp.seq_items = (int)seq_items;
+            kp.piece_items = (int)((seq_items + kp.pieces - 1) / kp.pieces);
+            kp.fd_vpr = make_fastdiv((uint32_t)(kp.row_bytes / 16));
+            kp.fd_R = make_fastdiv((uint32_t)kp.R);
+            kp.fd_H = make_fastdiv((uint32_t)kp.H);
+            // shared memory: the chunk stage (16-byte granular) + the parked rows of kCarryNI items per thread
+            const size_t stage_bytes = (smem + 15) / 16 * 16;
+            static const int smem_pad = [] {  // A/B: fewer resident CTAs per SM (smaller wave -> smaller lag -> smaller tail)
+                const char* e = getenv("SD_B200_STEP_SMEM_PAD");
+                return e ? atoi(e) : 0;
+            }();
+            static const int carry_env = [] {
+                const char* e = getenv("SD_B200_STEP_CARRY_NI");
+                return e ? atoi(e) : 0;
+            }();
+            int carry_ni = (kp.piece_items + threads - 1) / threads;
+            carry_ni = carry_ni < 1 ? 1 : (carry_ni > kCarryNI ? kCarryNI : carry_ni);
+            if (carry_env >= 1 && carry_env <= kCarryNI) carry_ni = carry_env;
+            kp.carry_ni = carry_ni;
+            const size_t smem_step = stage_bytes + (size_t)carry_ni * 2 * 16 * threads + (size_t)smem_pad;
+            int tail_park_items = (int)(smem_step / ((size_t)2 * 16 * threads));
+            static const int tail_items_env = [] {
+                const char* e = getenv("SD_B200_STEP_TAIL_ITEMS");
+                return e ? atoi(e) : 0;
+            }();
+            if (tail_items_env > 0 && tail_items_env < tail_park_items) tail_park_items = tail_items_env;
+            kp.tail_pieces = (int)((seq_items + (long long)tail_park_items * threads - 1) / ((long long)tail_park_items * threads));
+            if (kp.tail_pieces < 1) kp.tail_pieces = 1;
+            // Lag: far enough that a carrying CTA finds the word of its sequence published when it starts (one
+            // wave of resident CTAs plus the finalizer's latency), i.e. about 1.5 waves' worth of sequences.
+            int lag = g_fused_lag;
+            if (lag <= 0) {
+                static const int lag_pct = [] {  // A/B: lag as a percentage of one wave of resident CTAs (default 150)
+                    const char* e = getenv("SD_B200_STEP_LAG_PCT");
+                    return e ? atoi(e) : 150;
+                }();
+                const long long resident = (long long)step_occupancy(logit_dtype, threads, smem_step) * sm_count();
+                lag = (int)((resident * lag_pct / 100 + kp.pieces - 1) / kp.pieces);
+                if (lag < 1) lag = 1;
+            }
+            if (lag > B) lag = B;
+            kp.lag = lag;
+            const unsigned n_tail = (unsigned)lag * (unsigned)kp.tail_pieces;
+            kp.total_ctas = n_tail;
+            static const int l2pf = [] {  // A/B (default off: measured no gain, the tail is bandwidth-bound, not latency-bound)
+                const char* e = getenv("SD_B200_STEP_L2_PREFETCH");
+                return (e && e[0] == '1') ? 1 : 0;
+            }();
+            kp.l2_prefetch = l2pf;
+            static const int stagger = [] {
+                const char* e = getenv("SD_B200_STEP_STAGGER_NS");
+                return e ? atoi(e) : 0;
+            }();
+            kp.stagger_ns = stagger;
+            p.words = kp.flags;
+            p.epoch_word = kp.epoch_word;
+            p.seq_lens = kp.seq_lens_out;
+            p.kv_overflow = kp.overflow;
+            p.kv_capacity = kp.capacity;
+            p.kv_R = kp.R;
+            p.word_release = kp.xchg_packed ? 1 : 0;
+            p.seq_ready = nullptr;
+            static const int eager = [] {
+                const char* e = getenv("SD_B200_STEP_EAGER_ROWS");
+                return (e && e[0] == '1') ? 1 : 0;
+            }();
+            kp.eager_rows = eager;
+            if (g_trace && (size_t)(grid + n_tail) <= g_trace_ctas) p.trace = g_trace;
+            return to_status(launch_step(p, kp, logit_dtype, grid + n_tail, (int)grid, threads, stage_bytes, smem_step, tail_park_items, st));
+        }
         const unsigned total = grid + fused_gx * (unsigned)fused_kv->n_layers;
-        // RB <= 3 rows of K and V in flight per append thread keeps the fused kernel at <= 64 registers, i.e. four
-        // resident CTAs per SM for the verify part (at RB = 5 it needs 80 registers: three CTAs, 35 % occupancy)
+        // RB <= 3 rows of K and V in flight per append thread keeps the kernel at <= 64 registers (4 CTAs per SM)
         const int rb = fused_rb > 3 ? 3 : fused_rb;
         return to_status(launch_fused(p, *fused_kv, logit_dtype, rb, total, (int)grid, (int)fused_gx, threads, smem, st));
     }
@@ -1191,6 +1376,8 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
     }
     return to_status(e);
 }
+
+int verify_tu_spin_error(int clear, unsigned* out) { return tu_spin_error(clear, out); }
 
 }  // namespace sd
 
@@ -1242,23 +1429,25 @@ int sd_verify_prefix(const void* logits, int logit_dtype, int64_t stride_b, int6
                           nullptr, nullptr, nullptr, workspace, workspace_bytes, B, rows, K, V, stream, exchange, seq_ready);
 }
 
-int sd_verify_append_set_copy_all(int enabled) {
-    sd::g_fused_copy_all = enabled ? 1 : 0;
+int sd_verify_append_set_mode(int mode, int lag) {
+    if (mode < 0 || mode > 1 || lag < 0 || lag > 4096) return SD_ERR_INVALID_ARG;
+    sd::g_fused_mode = mode;
+    sd::g_fused_lag = lag;
     return SD_OK;
 }
 
-int sd_verify_append_set_interleave(int enabled) {
-    sd::g_fused_interleave = enabled ? 1 : 0;
-    return SD_OK;
-}
+size_t sd_step_state_bytes(int B) { return B > 0 ? (size_t)B * 8 + 8 : 8; }
 
 int sd_verify_append(const sd_step_args* a, void* stream) {
     using namespace sd;
     if (!a) return SD_ERR_INVALID_ARG;
     if (a->rows != a->K + 1) return SD_ERR_SHAPE;  // the append keeps accept_len + 1 of the K + 1 offered rows
-    if (!a->seq_ready || !a->accept_len) return SD_ERR_INVALID_ARG;
+    if (!a->accept_len || !a->ticket) return SD_ERR_INVALID_ARG;
+    const int mode = g_fused_mode;
+    if (mode == 0 && (!a->step_state || reinterpret_cast<uintptr_t>(a->step_state) % 8)) return SD_ERR_INVALID_ARG;
+    if (mode == 1 && !a->seq_ready) return SD_ERR_INVALID_ARG;
     // With an exchange the records are pushed either by the append part (exchange_push_in_append) or by the verify
-    // finalizers; in both cases the first append CTA gathers them, after every finalizer of this launch has read
+    // finalizers; in both cases one append CTA gathers them, after every finalizer of this launch has read
     // the epoch (sd_kv_col.cuh -- the missing wait was the multi-GPU stall of round 1, tools/repro_epoch_race.py).
     if (a->exchange && !a->packed) return SD_ERR_INVALID_ARG;
     if (a->B <= 0) return SD_OK;
@@ -1270,10 +1459,16 @@ int sd_verify_append(const sd_step_args* a, void* stream) {
                             a->accept_len, 1, a->zero_rejected, a->max_seq_len_host, a->overflow_flag, a->ticket, a->exchange,
                             a->exchange_out, a->exchange_push_in_append ? a->packed : nullptr, a->seq_ready, &kp, &gx, &rb);
     if (rc != SD_OK) return rc;
-    {
-        // Experiment switch (default off, next-round A/B): request the first rows of K and V BEFORE the per-sequence
-        // flag wait.  Legal in this launch -- the staged rows are its inputs -- and it takes one dependent round
-        // trip off every append CTA; the combination with the flags has no GPU test yet, hence not the default.
+    if (a->layer_stride_arena != 0 || a->layer_stride_new != 0) {
+        if (!a->layer0.arena_k || !a->layer0.arena_v || !a->layer0.new_k || !a->layer0.new_v) return SD_ERR_INVALID_ARG;
+        if (a->layer_stride_arena % 16 || a->layer_stride_new % 16) return SD_ERR_ALIGNMENT;
+        kp.uniform = 1;
+        kp.layer0 = a->layer0;
+        kp.ls_arena = a->layer_stride_arena;
+        kp.ls_new = a->layer_stride_new;
+    }
+    if (mode == 1) {
+        // A/B switch of the round-1 layout: request the first rows of K and V BEFORE the per-sequence flag wait
         static const int early = [] {
             const char* e = getenv("SD_B200_FUSED_EARLY_ROWS");
             return (e && e[0] == '1') ? 1 : 0;
@@ -1283,8 +1478,8 @@ int sd_verify_append(const sd_step_args* a, void* stream) {
     return run_verify(false, a->logits, a->logit_dtype, a->stride_b, a->stride_r, a->draft_ids, a->id_dtype, a->id_stride_b,
                       SD_ACCEPT_GREEDY, 0.f, 1.f, a->accept_len, a->accepted_mask, a->target_ids, a->bonus, a->packed, nullptr,
                       nullptr, nullptr, a->workspace, a->workspace_bytes, a->B, a->rows, a->K, a->V, stream,
-                      a->exchange_push_in_append ? nullptr : a->exchange, a->seq_ready, &kp, gx, rb,
-                      (g_fused_copy_all && !a->exchange) ? reinterpret_cast<unsigned*>(a->group_counters) : nullptr);
+                      a->exchange_push_in_append ? nullptr : a->exchange, mode == 1 ? a->seq_ready : nullptr, &kp, gx, rb,
+                      mode == 0 ? a->step_state : nullptr);
 }
 
 int sd_verify_step(const void* logits, int logit_dtype, int64_t stride_b, int64_t stride_r,

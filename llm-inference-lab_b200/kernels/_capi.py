@@ -18,7 +18,7 @@ from . import build as _build
 DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
 ID_I32, ID_I64 = 0, 1
 ACCEPT_GREEDY, ACCEPT_TYPICAL, ACCEPT_CONFIDENCE, ACCEPT_TOPK = 0, 1, 2, 3
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _vp = C.c_void_p
 _i = C.c_int
@@ -38,8 +38,9 @@ SIGNATURES = {
     "sd_verify_prefix": (_i, [_vp, _i, _i64, _i64, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                               _i, _i, _i, _i, _vp, _vp, _vp]),
     "sd_verify_append": (_i, [_vp, _vp]),
-    "sd_verify_append_set_interleave": (_i, [_i]),
-    "sd_verify_append_set_copy_all": (_i, [_i]),
+    "sd_verify_append_set_mode": (_i, [_i, _i]),
+    "sd_step_state_bytes": (_sz, [_i]),
+    "sd_device_error": (_i, [_i, C.POINTER(C.c_uint)]),
     "sd_verify_step": (_i, [_vp, _i, _i64, _i64, _vp, _i, _i64, _i, _f, _f, _vp, _vp, _vp, _vp, _vp,
                             _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sd_exchange_bytes": (_sz, [_i, _i, _i]),
@@ -81,6 +82,12 @@ class ExchangeDesc(C.Structure):
                 ("total_rows", C.c_int32), ("lag", C.c_int32), ("reserved", C.c_int32 * 2), ("peer", C.c_void_p * MAX_PEERS)]
 
 
+class KvLayer(C.Structure):
+    """struct sd_kv_layer (include/sd_verify.h)."""
+
+    _fields_ = [("arena_k", C.c_void_p), ("arena_v", C.c_void_p), ("new_k", C.c_void_p), ("new_v", C.c_void_p)]
+
+
 class StepArgs(C.Structure):
     """struct sd_step_args (include/sd_verify.h)."""
 
@@ -95,7 +102,8 @@ class StepArgs(C.Structure):
         ("row_bytes", C.c_int64), ("capacity", C.c_int64), ("arena_stride_b", C.c_int64), ("arena_stride_h", C.c_int64),
         ("new_stride_b", C.c_int64), ("new_stride_h", C.c_int64), ("new_stride_r", C.c_int64), ("max_seq_len_host", C.c_int64),
         ("seq_lens", C.c_void_p), ("overflow_flag", C.c_void_p), ("ticket", C.c_void_p), ("seq_ready", C.c_void_p),
-        ("exchange", C.c_void_p), ("exchange_out", C.c_void_p), ("group_counters", C.c_void_p),
+        ("exchange", C.c_void_p), ("exchange_out", C.c_void_p), ("step_state", C.c_void_p),
+        ("layer0", KvLayer), ("layer_stride_arena", C.c_int64), ("layer_stride_new", C.c_int64),
     ]
 
 

@@ -523,7 +523,10 @@ def verify_append_launch(
     a.seq_ready = seq_ready.data_ptr()
     a.exchange = exchange.desc_ptr if exchange is not None else None
     a.exchange_out = exchange.out.data_ptr() if exchange is not None else None
-    a.group_counters = arena.group_counters().data_ptr()
+    a.step_state = arena.step_state().data_ptr()
+    uni = arena.uniform_layers()
+    if uni is not None:  # one [layers, ...] allocation: layer pointers by arithmetic, no table lookup on the device
+        (a.layer0.arena_k, a.layer0.arena_v, a.layer0.new_k, a.layer0.new_v), a.layer_stride_arena, a.layer_stride_new = uni
     lib = _capi.lib()
     dev = logits.device
     with torch.cuda.device(dev):
@@ -652,9 +655,20 @@ def set_attention_tuning(config: int = 0) -> None:
     _capi.lib().check(_capi.lib().sd_verify_attention_set_tuning(config), "sd_verify_attention_set_tuning")
 
 
-def set_fused_copy_all(enabled: bool = True) -> None:
-    """Copy-all mode of the fused step (include/sd_verify.h: sd_verify_append_set_copy_all)."""
-    _capi.lib().check(_capi.lib().sd_verify_append_set_copy_all(int(enabled)), "sd_verify_append_set_copy_all")
+def set_fused_mode(mode: int = 0, lag: int = 0) -> None:
+    """Layout of the fused step (include/sd_verify.h: sd_verify_append_set_mode): 0 = lagged append (default),
+    1 = the round-1 layout (append CTAs behind all verify CTAs), kept for A/B evidence."""
+    _capi.lib().check(_capi.lib().sd_verify_append_set_mode(int(mode), int(lag)), "sd_verify_append_set_mode")
+
+
+def device_error(clear: bool = True) -> int:
+    """OR of the bounded device-side waits that expired since the last clear (include/sd_verify.h:
+    sd_device_error); 0 = none.  Synchronises the device."""
+    import ctypes as C
+
+    v = C.c_uint(0)
+    _capi.lib().check(_capi.lib().sd_device_error(int(clear), C.byref(v)), "sd_device_error")
+    return int(v.value)
 
 
 def set_pdl(enabled: bool = True) -> None:

@@ -50,14 +50,31 @@ class KVArena:
         self.layer_table = self._build_table(self.new_k, self.new_v)
         self._max_len_host = 0  # host-side upper bound of seq_lens, for the capacity check
 
-    def group_counters(self) -> torch.Tensor:
-        """Zero-initialised counters for the copy-all fused step (2 per append x-slot; the kernel re-zeroes them)."""
-        if getattr(self, "_group_counters", None) is None:
-            slots = self.batch * self.n_kv_heads * (self.row_bytes // 16)
-            self._group_counters = torch.zeros(2 * ((slots + 255) // 256) + 2, dtype=torch.int32, device=self.device)
-        return self._group_counters
+    def step_state(self) -> torch.Tensor:
+        """Device state of the fused step (include/sd_verify.h, sd_step_args.step_state): one 8-byte word per
+        sequence + the launch epoch.  Zero once; the kernels never need it re-armed."""
+        if getattr(self, "_step_state", None) is None:
+            n = int(cuda_ops._capi.lib().sd_step_state_bytes(self.batch))
+            self._step_state = torch.zeros((n + 7) // 8, dtype=torch.int64, device=self.device)
+        return self._step_state
 
     # -- layout helpers -------------------------------------------------------------------------
+    def use_staging(self, new_k: torch.Tensor, new_v: torch.Tensor, table: Optional[torch.Tensor] = None) -> None:
+        """Point the arena at another pair of staged-row tensors [layers, B, Hkv, R, D] (e.g. the output buffers of
+        the target forward); ``table`` = a prebuilt ``_build_table(new_k, new_v)`` (built here when omitted)."""
+        assert new_k.shape == self.new_k.shape and new_v.shape == self.new_v.shape and new_k.stride() == new_v.stride()
+        self.new_k, self.new_v = new_k, new_v
+        self.layer_table = table if table is not None else self._build_table(new_k, new_v)
+
+    def uniform_layers(self):
+        """((arena_k0, arena_v0, new_k0, new_v0), arena layer stride, staging layer stride) in bytes when every
+        layer sits at a fixed stride from layer 0 (this class always allocates that way), else None."""
+        es = self.k.element_size()
+        sa, sn = self.k.stride(0) * es, self.new_k.stride(0) * es
+        if self.n_layers > 1 and (sa % 16 or sn % 16 or self.v.stride(0) * es != sa or self.new_v.stride(0) * es != sn):
+            return None
+        return (self.k.data_ptr(), self.v.data_ptr(), self.new_k.data_ptr(), self.new_v.data_ptr()), sa, sn
+
     def _build_table(self, new_k: torch.Tensor, new_v: torch.Tensor) -> torch.Tensor:
         rows = [
             [self.k[l].data_ptr(), self.v[l].data_ptr(), new_k[l].data_ptr(), new_v[l].data_ptr()]

@@ -124,18 +124,30 @@ class VerifyStep:
 
     # -- CUDA graph (reference: src/specdec/utils/graph_capture.py:49-99 GraphCapture, never wired in) --
     def capture(self) -> None:
+        """Record the step into a CUDA graph.  A warm-up run (module load, kernel attributes) precedes the capture;
+        it is made side-effect free for the KV arena: lengths, overflow flag and the host-side length bound are
+        restored afterwards (the rows it wrote lie beyond the restored lengths and are overwritten by the first
+        real step).  With a multi-GPU exchange the warm-up is a real exchange step on every rank (collective)."""
         torch.cuda.synchronize(self.device)
+        saved = None
+        if self.arena is not None:
+            saved = (self.arena.seq_lens.clone(), self.arena.overflow.clone(), self.arena._max_len_host)
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            self.run()  # warm-up outside capture (module load, attribute setup)
+            self.run()  # warm-up outside capture
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
-        if self.arena is not None:
-            self._lens_before_capture = self.arena.seq_lens.clone()
+        if saved is not None:
+            self.arena.seq_lens.copy_(saved[0])
+            self.arena.overflow.copy_(saved[1])
+            self.arena._max_len_host = saved[2]
+            torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self.run()
+        if saved is not None:
+            self.arena._max_len_host = saved[2]  # (the capture pass advanced the host bound without running)
         self.graph = g
 
     def replay(self) -> None:

@@ -77,5 +77,5 @@ def test_ctypes_mirrors_match_the_c_struct_layout():
     assert lib.sd_struct_layout(4) == _capi.StepArgs.layers.offset
     assert lib.sd_struct_layout(5) == _capi.StepArgs.row_bytes.offset
     assert lib.sd_struct_layout(6) == _capi.StepArgs.seq_lens.offset
-    assert lib.sd_struct_layout(7) == _capi.StepArgs.group_counters.offset
+    assert lib.sd_struct_layout(7) == _capi.StepArgs.step_state.offset
     assert lib.sd_struct_layout(99) == 0

@@ -30,6 +30,43 @@ def test_batch_verify_on_the_verification_stream(use_graph):
     sched.cleanup()
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_batch_verify_with_arena_appends_once_per_step(use_graph):
+    """the first graphed step must not run twice -- capture()'s warm-up is side-effect free for
+    the arena, so lengths and rows match the oracle from the first step on."""
+    from specdec.cache.kv_arena import KVArena
+
+    sched = create_speculative_scheduler("cuda")
+    B, K, V, layers, H, D, L, cap = 6, 4, 8009, 3, 2, 64, 5, 64
+    arena = KVArena(layers, B, H, D, cap, K + 1, torch.bfloat16, "cuda")
+    g = torch.Generator().manual_seed(7)
+    arena.k[:, :, :, :L] = torch.randn(layers, B, H, L, D, generator=g).to(torch.bfloat16).cuda()
+    arena.v[:, :, :, :L] = torch.randn(layers, B, H, L, D, generator=g).to(torch.bfloat16).cuda()
+    arena.set_lengths([L] * B)
+    exp_k, exp_v = to_np(arena.k).copy(), to_np(arena.v).copy()
+    lens = np.full(B, L, np.int32)
+    for it in range(4):
+        logits, ids = make_verify_inputs(B, K + 1, K, V, "bf16", p_match=0.7, seed=40 + it, device="cuda")
+        arena.new_k.copy_(torch.randn(arena.new_k.shape, generator=g).to(torch.bfloat16))
+        arena.new_v.copy_(torch.randn(arena.new_v.shape, generator=g).to(torch.bfloat16))
+        step = sched.schedule_batch_verify(logits, ids, arena=arena, use_graph=use_graph)
+        torch.cuda.synchronize()
+        acc, _, _, _ = c_oracle.verify(to_np(logits), "bf16", to_np(ids))
+        nk, nv = to_np(arena.new_k), to_np(arena.new_v)
+        for l in range(layers):
+            new_lens = c_oracle.kv_arena_append(exp_k[l], lens, nk[l], acc + 1, True)
+            c_oracle.kv_arena_append(exp_v[l], lens, nv[l], acc + 1, True)
+        lens = new_lens
+        np.testing.assert_array_equal(step.accept_len.cpu().numpy(), acc)
+        np.testing.assert_array_equal(arena.seq_lens.cpu().numpy(), lens, err_msg=f"step {it}")
+        # rows below the valid lengths are exact (the graph warm-up may have left rows BEYOND them at step 0)
+        got_k, got_v = to_np(arena.k), to_np(arena.v)
+        for b in range(B):
+            np.testing.assert_array_equal(got_k[:, b, :, : lens[b]], exp_k[:, b, :, : lens[b]])
+            np.testing.assert_array_equal(got_v[:, b, :, : lens[b]], exp_v[:, b, :, : lens[b]])
+    sched.cleanup()
+
+
 class _ToyModel:
     """Duck-typed model for the reference API: returns planted tokens / logits."""
 

@@ -40,8 +40,8 @@ def test_multi_step_matches_oracle(use_graph):
     exp_k, exp_v = to_np(arena.k).copy(), to_np(arena.v).copy()
     lens = arena.seq_lens.cpu().numpy().copy()
     if use_graph:
-        step.capture()
-        arena.set_lengths(lens)          # capture's warm-up run advanced the lengths
+        step.capture()                   # warm-up leaves lengths untouched; its rows lie beyond them
+        np.testing.assert_array_equal(arena.seq_lens.cpu().numpy(), lens)
         arena.k.copy_(torch.from_numpy(exp_k.view(np.int16)).view(torch.bfloat16))
         arena.v.copy_(torch.from_numpy(exp_v.view(np.int16)).view(torch.bfloat16))
     for it in range(6):
@@ -281,7 +281,7 @@ def test_peer_exchange_pushed_and_gathered_by_the_append_launch():
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
-@pytest.mark.parametrize("overlap", [True, False, "copy_all"])
+@pytest.mark.parametrize("overlap", [True, False, "r1_layout", "lag1", "lag3", "lag64"])
 def test_append_overlapping_the_verify_tail(use_graph, overlap):
     """Per-sequence flags (seq_ready): the append starts on a sequence as soon as that sequence is verified.
     Same results as the serialised form, over many steps (flags re-armed every step), Llama-like row size."""
@@ -293,35 +293,42 @@ def test_append_overlapping_the_verify_tail(use_graph, overlap):
     arena.v[:, :, :, :L] = torch.randn(layers, B, H, L, D, generator=g).to(torch.bfloat16).cuda()
     arena.set_lengths([L] * B)
     step = VerifyStep(B, K, V, arena=arena, device=dev)
-    copy_all = overlap == "copy_all"  # fused step whose append CTAs copy all rows up front; finalizers zero + commit
+    # True = ONE launch, lagged append (heuristic lag); lagN = the same with N sequences of lag (64 > B: every
+    # piece in the tail); r1_layout = ONE launch, append CTAs behind all verify CTAs; False = two launches
     step.overlap_append = bool(overlap)
     from kernels import cuda_ops as _ops
 
-    _ops.set_fused_copy_all(copy_all)
-    exp_k, exp_v = to_np(arena.k).copy(), to_np(arena.v).copy()
-    lens = np.full(B, L, np.int32)
-    if use_graph:
-        step.capture()
-        arena.set_lengths([L] * B)
-        arena.k.copy_(torch.from_numpy(exp_k.view(np.int16)).view(torch.bfloat16))
-        arena.v.copy_(torch.from_numpy(exp_v.view(np.int16)).view(torch.bfloat16))
-    for it in range(6):
-        logits, ids = make_verify_inputs(B, K + 1, K, V, "bf16", p_match=0.75, seed=900 + it, device="cuda")
-        step.logits.copy_(logits)
-        step.draft_ids.copy_(ids)
-        arena.new_k.copy_(torch.randn(arena.new_k.shape, generator=g).to(torch.bfloat16))
-        arena.new_v.copy_(torch.randn(arena.new_v.shape, generator=g).to(torch.bfloat16))
-        torch.cuda.synchronize()
-        step.replay() if use_graph else step.run()
-        torch.cuda.synchronize()
-        acc, mask, tgt, bonus, lens = _oracle_step(exp_k, exp_v, lens, logits, ids, to_np(arena.new_k), to_np(arena.new_v))
-        np.testing.assert_array_equal(step.accept_len.cpu().numpy(), acc)
-        np.testing.assert_array_equal(arena.seq_lens.cpu().numpy(), lens)
-        np.testing.assert_array_equal(to_np(arena.k), exp_k)
-        np.testing.assert_array_equal(to_np(arena.v), exp_v)
-        assert int(step.seq_ready.sum()) == 0  # re-armed
-        assert int(arena.group_counters().sum()) == 0
-    _ops.set_fused_copy_all(False)
+    if overlap == "r1_layout":
+        _ops.set_fused_mode(1, 0)
+    elif isinstance(overlap, str):
+        _ops.set_fused_mode(0, int(overlap[3:]))
+    try:
+        exp_k, exp_v = to_np(arena.k).copy(), to_np(arena.v).copy()
+        lens = np.full(B, L, np.int32)
+        if use_graph:
+            step.capture()
+            arena.set_lengths([L] * B)
+            arena.k.copy_(torch.from_numpy(exp_k.view(np.int16)).view(torch.bfloat16))
+            arena.v.copy_(torch.from_numpy(exp_v.view(np.int16)).view(torch.bfloat16))
+        for it in range(6):
+            logits, ids = make_verify_inputs(B, K + 1, K, V, "bf16", p_match=0.75, seed=900 + it, device="cuda")
+            step.logits.copy_(logits)
+            step.draft_ids.copy_(ids)
+            arena.new_k.copy_(torch.randn(arena.new_k.shape, generator=g).to(torch.bfloat16))
+            arena.new_v.copy_(torch.randn(arena.new_v.shape, generator=g).to(torch.bfloat16))
+            torch.cuda.synchronize()
+            step.replay() if use_graph else step.run()
+            torch.cuda.synchronize()
+            acc, mask, tgt, bonus, lens = _oracle_step(exp_k, exp_v, lens, logits, ids, to_np(arena.new_k), to_np(arena.new_v))
+            np.testing.assert_array_equal(step.accept_len.cpu().numpy(), acc)
+            np.testing.assert_array_equal(arena.seq_lens.cpu().numpy(), lens)
+            np.testing.assert_array_equal(to_np(arena.k), exp_k)
+            np.testing.assert_array_equal(to_np(arena.v), exp_v)
+            assert int(step.seq_ready.sum()) == 0  # re-armed
+            assert int(arena._ticket.item()) == 0
+    finally:
+        _ops.set_fused_mode(0, 0)
+    assert _ops.device_error() == 0
 
 
 @pytest.mark.parametrize("world", [1, 2])
