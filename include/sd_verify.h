@@ -124,6 +124,15 @@ int sd_exchange_free(void* ptr);
  * them to out [world * rows_per_rank, width] int32 (nullable) and advance the epoch.  One small
  * kernel on `stream`; call it once per verify launch that carried `exchange`. */
 int sd_exchange_wait(const sd_exchange* exchange, int32_t* out, void* stream);
+/* Start gate: one tiny kernel on `stream` behind which the work enqueued after it starts (a) only once the host has
+ * stored go_value into *host_go (nullable; a uint32 in pinned, device-accessible host memory -- set it after the
+ * work behind the gate has been enqueued, so the GPU never outruns its launch queue), and (b) only once every rank
+ * of `exchange` (nullable = single GPU) has reached the same gate: each rank stores an arrival word into every
+ * peer's header and polls its own.  Ranks then leave the gate within ~2 us of each other whatever the skew of
+ * their host threads was -- a lock-step multi-GPU loop (lag 0 exchange) otherwise absorbs that skew in its first
+ * gather.  Collective over the ranks of the exchange; waits are bounded (sd_device_error, site 16).  No reference
+ * counterpart (single GPU). */
+int sd_start_gate(const sd_exchange* exchange, const void* host_go, unsigned go_value, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Kernel 1: fused verify.

@@ -12,6 +12,51 @@ __global__ void __launch_bounds__(256) exchange_wait_kernel(const sd_exchange* x
     exchange_gather_cta(x, out);
 }
 
+// Start gate (sd_start_gate): one warp.  (1) wait until the HOST has raised *host_go to go_value -- the caller sets it
+// after everything behind the gate has been enqueued, so no rank's GPU outruns its own launch queue; (2) tell every
+// peer "rank r has arrived at gate g" with one 8-byte store into its header, wait for every peer's word; (3) advance
+// the gate counter.  After the gate all ranks proceed within an NVLink store + poll of each other (~2 us), whatever
+// the skew of their host threads was.  Exchange header (first 256 bytes of the buffer): [0] u32 exchange epoch,
+// [16] u32 gate counter, [64 + 8 r] u64 arrival word of rank r (monotonic: gate + 1).
+__global__ void __launch_bounds__(32) start_gate_kernel(const sd_exchange* x, const unsigned* host_go, const unsigned go_value) {
+    pdl_wait();
+    pdl_trigger();
+    const int lane = threadIdx.x;
+    if (host_go && lane == 0) {
+        SpinGuard guard;
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(host_go) : "memory");
+            if (v == go_value) break;
+            if (!guard.keep_waiting(kSpinStartGate)) break;
+            __nanosleep(200);
+        }
+    }
+    __syncwarp();
+    if (!x) return;
+    char* own = reinterpret_cast<char*>(x->peer[x->rank]);
+    unsigned gate;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(gate) : "l"(own + 16) : "memory");
+    const unsigned long long want = (unsigned long long)gate + 1ull;
+    for (int r = lane; r < x->world; r += 32) {
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(x->peer[r]) + 64 + 8 * x->rank);
+        asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(want) : "memory");
+    }
+    for (int r = lane; r < x->world; r += 32) {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(own + 64 + 8 * r);
+        SpinGuard guard;
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+            if (v >= want) break;
+            if (!guard.keep_waiting(kSpinStartGate)) break;
+            __nanosleep(100);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<volatile unsigned*>(own + 16) = gate + 1u;
+}
+
 int exchange_tu_spin_error(int clear, unsigned* out) { return tu_spin_error(clear, out); }
 
 }  // namespace sd
@@ -57,6 +102,12 @@ int sd_exchange_close(void* peer_ptr) {
 int sd_exchange_free(void* ptr) {
     if (!ptr) return SD_OK;
     return sd::to_status(cudaFree(ptr));
+}
+
+int sd_start_gate(const sd_exchange* exchange, const void* host_go, unsigned go_value, void* stream) {
+    if (!exchange && !host_go) return SD_OK;
+    return sd::to_status(sd::launch_kernel(sd::start_gate_kernel, dim3(1), dim3(32), 0, reinterpret_cast<cudaStream_t>(stream),
+                                           exchange, reinterpret_cast<const unsigned*>(host_go), go_value));
 }
 
 int sd_exchange_wait(const sd_exchange* exchange, int32_t* out, void* stream) {

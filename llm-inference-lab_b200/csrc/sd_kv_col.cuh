@@ -514,9 +514,9 @@ SD_DEVINL void kv_piece_prefetch(const KvParams& p, const int seq, const int pie
 // first: its CTAs are dispatched (and have their rows parked) before its word can possibly be there, while the
 // CTAs dispatched last serve the sequences whose words have long been published and never wait.  `park_items`
 // items per thread parked in the CTA's whole shared memory, every offered row requested by the first instructions of
-// the CTA (no dependence on the word).  The last tail CTA to retire closes the launch: once every sequence word is
-// published -- i.e. every verify CTA has published its partial, before which it has consumed the epoch -- it serves
-// the multi-GPU exchange and advances the launch epoch.
+// the CTA (no dependence on the word).  Tail CTA 0 also serves the multi-GPU exchange.  The last tail CTA to retire
+// closes the launch: once every sequence word is published -- i.e. every verify CTA has published its partial,
+// before which it has consumed the epoch -- it advances the launch epoch.
 SD_DEVINL void kv_tail_body(const KvParams& p, const int t, unsigned long long* trace, uint4* park, const int park_items) {
     const int seq = p.B - 1 - t / p.tail_pieces, tp = t % p.tail_pieces;
     const unsigned tag = step_tag(p.epoch_word);
@@ -528,6 +528,18 @@ SD_DEVINL void kv_tail_body(const KvParams& p, const int t, unsigned long long* 
         piece_items_run(p, tag, seq, it0 + (int)threadIdx.x, it_end, word, park, park_items);
     }
     if (trace && threadIdx.x == 0) trace[1] = global_timer_ns();
+    if (p.xchg && t == 0) {
+        // Multi-GPU exchange, served by ONE tail CTA in parallel with the others' stores (not on the closing path).
+        // The gather ends by advancing the exchange epoch, which every local finalizer must have read first (it
+        // publishes its word after its push): wait for all words, not only this CTA's sequence.
+        wait_all_words(p, tag);
+        __syncthreads();
+        if (p.xchg_packed) {  // records pushed from here: the finalizers released them before publishing their words
+            __threadfence();
+            exchange_push_cta(p.xchg, p.xchg_packed, p.B);
+        }
+        exchange_gather_cta(p.xchg, p.xchg_out);
+    }
     __shared__ int s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -538,15 +550,6 @@ SD_DEVINL void kv_tail_body(const KvParams& p, const int t, unsigned long long* 
     if (!s_last) return;
     wait_all_words(p, tag);
     __syncthreads();
-    if (p.xchg) {
-        if (p.xchg_packed) {  // records pushed from here: the finalizers released them before publishing their words
-            __threadfence();
-            exchange_push_cta(p.xchg, p.xchg_packed, p.B);
-        }
-        // (the gather ends by advancing the exchange epoch, which every local finalizer has read: it publishes its
-        // word after its push)
-        exchange_gather_cta(p.xchg, p.xchg_out);
-    }
     if (threadIdx.x == 0) {
         unsigned e;
         asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(e) : "l"(p.epoch_word) : "memory");

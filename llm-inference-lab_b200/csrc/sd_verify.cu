@@ -395,10 +395,22 @@ SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int n
     __shared__ float s_ptok[64];
     // draft ids of this sequence: issued now, consumed by warp 0 after the row merge (K <= 64)
     int my_id[2] = {-1, -1};
+    // multi-GPU exchange: the descriptor fields and the exchange epoch are requested NOW (three dependent L2 round
+    // trips that hide behind the partial poll below) and only used once the record is final
+    int x_world = 0, x_width = 0, x_rank = 0, x_rpr = 0;
+    unsigned x_epoch = 0u;
     if (wid == 0) {
 #pragma unroll
         for (int h = 0; h < 2; ++h)
             if (h * 32 + lane < p.K) my_id[h] = load_id(p.ids, p.id_dtype, (int64_t)b * p.id_stride_b + h * 32 + lane);
+        if (p.xchg) {
+            const sd_exchange* x = p.xchg;
+            x_world = x->world;
+            x_width = x->width;
+            x_rank = x->rank;
+            x_rpr = x->rows_per_rank;
+            x_epoch = ld_volatile_u32(reinterpret_cast<const unsigned*>(x->peer[x_rank]));
+        }
     }
     for (int r = wid; r < p.rows; r += nwarps) {
         const int grow = b * p.rows + r;
@@ -473,8 +485,8 @@ SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int n
         }
     }
     cta_sync<NAMED>(nthreads);
+    int nacc = p.K;  // (meaningful in warp 0)
     if (wid == 0) {
-        int nacc = p.K;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int k = h * 32 + lane;
@@ -499,36 +511,19 @@ SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int n
             p.accept_len[b] = nacc;
             if (p.bonus) p.bonus[b] = p.rows > p.K ? s_tgt[nacc] : -1;
         }
-        if (p.xchg) {
-            // Fused result exchange: the record goes straight into every rank's buffer (NVLink stores on
-            // peer pointers).  Each value travels in ONE 8-byte store together with the epoch tag
-            // (LL-style: {epoch + 1, value}), so no fence, atomic or arrival counter is needed -- the
-            // consumer polls the words until their tag matches.
-            const sd_exchange* x = p.xchg;
-            const int world = x->world, width = x->width;
-            char* own = reinterpret_cast<char*>(x->peer[x->rank]);
-            const unsigned epoch = ld_volatile_u32(reinterpret_cast<const unsigned*>(own));
-            const unsigned long long tag = (unsigned long long)(epoch + 1u) << 32;
-            const size_t rec_row = (size_t)(epoch & 3u) * world * x->rows_per_rank + (size_t)x->rank * x->rows_per_rank + b;
-            for (int i = lane; i < world * width; i += 32) {
-                const int pr = i / width, col = i - pr * width;
-                int val = -1;
-                if (col == 0) val = nacc;
-                else if (col - 1 < p.rows) val = s_tgt[col - 1];
-                unsigned long long* recs =
-                    reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(x->peer[pr]) + kExchangeHeaderBytes);
-                recs[rec_row * width + col] = tag | (unsigned)val;  // weak store: posted, pipelined over NVLink
-            }
-        }
     }
+    // (a value that is 0 at run time but depends on the exchange epoch: folding it into the sequence word below makes the
+    // word's store wait for the epoch load -- "this finalizer has READ the exchange epoch" is then implied by its word)
+    const unsigned x_seen = x_epoch == 0xffffffffu ? 0x80000000u : 0u;
     if (wid == 0 && p.words) {
         // lagged fused step: publish {tag, n_keep, old length} in ONE 8-byte store and advance the length (this
-        // thread is the only reader and writer of seq_lens[b] in the launch).  After the peer push above, so a
-        // CTA that has seen every word knows every finalizer has read the exchange epoch.
+        // thread is the only reader and writer of seq_lens[b] in the launch).  BEFORE the peer push: the append of
+        // this sequence must not wait for NVLink stores; the exchange epoch was read above, which is all the
+        // gathering CTA needs to know before it advances that epoch.
         __syncwarp();
         if (lane == 0) {
             const int len = p.seq_lens ? p.seq_lens[b] : 0;
-            const int n_keep = p.accept_len[b] + 1;  // written by this thread a few lines above
+            const int n_keep = nacc + 1;
             int64_t room = p.kv_capacity - len;
             room = room < 0 ? 0 : (room > p.kv_R ? p.kv_R : room);
             int n = n_keep > p.kv_R ? p.kv_R : n_keep;
@@ -538,7 +533,25 @@ SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int n
             }
             if (p.seq_lens) p.seq_lens[b] = len + n;
             if (p.word_release) __threadfence();
-            st_volatile_u64(p.words + b, make_word(tag, n_keep > p.kv_R ? p.kv_R : n_keep, len));
+            st_volatile_u64(p.words + b, make_word(tag, n_keep > p.kv_R ? p.kv_R : n_keep, (int)((unsigned)len | x_seen)));
+        }
+    }
+    if (wid == 0 && p.xchg) {
+        // Fused result exchange: the record goes straight into every rank's buffer (NVLink stores on peer
+        // pointers).  Each value travels in ONE 8-byte store together with the epoch tag (LL-style:
+        // {epoch + 1, value}), so no fence, atomic or arrival counter is needed -- the consumer polls the words
+        // until their tag matches.
+        const sd_exchange* x = p.xchg;
+        const unsigned long long xtag = (unsigned long long)(x_epoch + 1u) << 32;
+        const size_t rec_row = (size_t)(x_epoch & 3u) * x_world * x_rpr + (size_t)x_rank * x_rpr + b;
+        for (int i = lane; i < x_world * x_width; i += 32) {
+            const int pr = i / x_width, col = i - pr * x_width;
+            int val = -1;
+            if (col == 0) val = nacc;
+            else if (col - 1 < p.rows) val = s_tgt[col - 1];
+            unsigned long long* recs =
+                reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(x->peer[pr]) + kExchangeHeaderBytes);
+            recs[rec_row * x_width + col] = xtag | (unsigned)val;  // weak store: posted, pipelined over NVLink
         }
     }
     if (wid == 0 && p.seq_ready) {

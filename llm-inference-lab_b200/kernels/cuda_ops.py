@@ -661,6 +661,30 @@ def set_fused_mode(mode: int = 0, lag: int = 0) -> None:
     _capi.lib().check(_capi.lib().sd_verify_append_set_mode(int(mode), int(lag)), "sd_verify_append_set_mode")
 
 
+class StartGate:
+    """Device-side start gate (include/sd_verify.h: sd_start_gate).  ``arm()`` enqueues the gate kernel on the current
+    stream; work enqueued after it starts only when ``release()`` has been called on the host AND (with a
+    ``scheduler.batch_shard.PeerExchange``) every rank has reached its own gate."""
+
+    def __init__(self, device, exchange=None) -> None:
+        self.device = torch.device(device)
+        self.exchange = exchange
+        self.flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.value = 0
+
+    def arm(self, hold: bool = True) -> None:
+        self.value += 1
+        if not hold:
+            self.flag[0] = self.value
+        with torch.cuda.device(self.device):
+            rc = _capi.lib().sd_start_gate(self.exchange.desc_ptr if self.exchange is not None else None,
+                                           self.flag.data_ptr(), self.value, _stream_ptr(self.device))
+        _capi.lib().check(rc, "sd_start_gate")
+
+    def release(self) -> None:
+        self.flag[0] = self.value
+
+
 def device_error(clear: bool = True) -> int:
     """OR of the bounded device-side waits that expired since the last clear (include/sd_verify.h:
     sd_device_error); 0 = none.  Synchronises the device."""
