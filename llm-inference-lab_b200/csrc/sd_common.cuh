@@ -228,7 +228,10 @@ SD_DEVINL void exchange_push_cta(const sd_exchange* x, const int32_t* packed, in
     }
 }
 
-SD_DEVINL void exchange_gather_cta(const sd_exchange* x, int32_t* out) {
+// Gather, split in two so that a caller can put a wait between the data movement and the epoch advance:
+// exchange_gather_records polls + copies the records of epoch (current - lag) and returns the current epoch;
+// exchange_advance publishes epoch + 1.  Both are called by a whole CTA.
+SD_DEVINL unsigned exchange_gather_records(const sd_exchange* x, int32_t* out) {
     char* own = reinterpret_cast<char*>(x->peer[x->rank]);
     unsigned epoch;
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(epoch) : "l"(own) : "memory");
@@ -271,8 +274,17 @@ SD_DEVINL void exchange_gather_cta(const sd_exchange* x, int32_t* out) {
             }
         }
     }
+    return epoch;
+}
+
+SD_DEVINL void exchange_advance(const sd_exchange* x, const unsigned epoch) {
     __syncthreads();
-    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(own) = epoch + 1u;
+    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(reinterpret_cast<char*>(x->peer[x->rank])) = epoch + 1u;
+}
+
+SD_DEVINL void exchange_gather_cta(const sd_exchange* x, int32_t* out) {
+    const unsigned epoch = exchange_gather_records(x, out);
+    exchange_advance(x, epoch);
 }
 
 // host side: OR of the spin sites that ran out of budget in THIS translation unit's kernels since the last clear

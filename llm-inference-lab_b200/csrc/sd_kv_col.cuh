@@ -530,15 +530,19 @@ SD_DEVINL void kv_tail_body(const KvParams& p, const int t, unsigned long long* 
     if (trace && threadIdx.x == 0) trace[1] = global_timer_ns();
     if (p.xchg && t == 0) {
         // Multi-GPU exchange, served by ONE tail CTA in parallel with the others' stores (not on the closing path).
-        // The gather ends by advancing the exchange epoch, which every local finalizer must have read first (it
-        // publishes its word after its push): wait for all words, not only this CTA's sequence.
-        wait_all_words(p, tag);
-        __syncthreads();
+        // The records arrive progressively (a finalizer pushes right after publishing its word), so the gather
+        // starts polling NOW and only the last few words are waited for.  The exchange epoch may advance only when
+        // every local finalizer has read it: with lag 0 that is implied by the gather itself (it has collected this
+        // rank's own records of the epoch, each tagged by its finalizer); with lag 1 wait for the words.
         if (p.xchg_packed) {  // records pushed from here: the finalizers released them before publishing their words
+            wait_all_words(p, tag);
+            __syncthreads();
             __threadfence();
             exchange_push_cta(p.xchg, p.xchg_packed, p.B);
         }
-        exchange_gather_cta(p.xchg, p.xchg_out);
+        const unsigned xepoch = exchange_gather_records(p.xchg, p.xchg_out);
+        if (p.xchg->lag != 0 || p.xchg_packed) wait_all_words(p, tag);
+        exchange_advance(p.xchg, xepoch);
     }
     __shared__ int s_last;
     __syncthreads();
