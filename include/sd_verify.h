@@ -398,8 +398,13 @@ int sd_kv_set_variant(int variant);
  * scale    softmax scale (1/sqrt(D) when <= 0)
  * n_splits 0 = heuristic (wave-quantised cost model on max_seq_len_host, bounded by the workspace);
  *          > 1 needs sd_verify_attention_workspace_bytes(..., n_splits) bytes
- * max_seq_len_host  upper bound of seq_lens known on the host (-1 = derive from kv_stride_h); only the
- *          split heuristic uses it -- the kernel reads the true lengths from seq_lens
+ * max_seq_len_host  upper bound of seq_lens known on the host (-1 = derive from kv_stride_h); the split heuristic
+ *          uses it -- the kernel reads the true lengths from seq_lens -- and max_seq_len_host + R > capacity is
+ *          refused (SD_ERR_CAPACITY)
+ * capacity  rows per (b, kv head) slab of the arena, C (<= 0: kv_stride_h / (D * elt)).  On the device
+ *          seq_lens[b] + R is clamped to it (a sequence can sit AT capacity after an append that overflowed): rows of
+ *          the next head are never read.  overflow_flag (nullable, int32) is set when a length was clamped or negative;
+ *          that sequence's output is then not meaningful.
  * Returns SD_ERR_UNSUPPORTED for dtype f32, D not in {64,128} or R beyond the limits above.
  * Algorithmic traffic: 2 * B * Hkv * (mean len + R) * D * elt bytes of KV read once per launch.
  * One launch (+ one small merge launch when n_splits > 1).
@@ -409,7 +414,7 @@ int sd_verify_attention(const void* q, const void* k_arena, const void* v_arena,
                         const int32_t* seq_lens, void* out, void* workspace,
                         size_t workspace_bytes, int dtype, int B, int Hq, int Hkv, int R, int D,
                         int64_t kv_stride_b, int64_t kv_stride_h, int64_t max_seq_len_host,
-                        float scale, int n_splits, void* stream);
+                        int64_t capacity, int32_t* overflow_flag, float scale, int n_splits, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Kernel 4: batched bonus-token sampler.

@@ -34,6 +34,8 @@ struct AttnParams {
     float* part_o;   // [rows_total, n_splits, D]
     float* part_ml;  // [rows_total, n_splits, 2]
     int64_t kv_stride_b, kv_stride_h;
+    int capacity;          // rows per (b, kv head) of the arena: seq_lens[b] + R is clamped to it
+    int32_t* overflow;     // nullable: set when a length had to be clamped (or was negative)
     int B, Hq, Hkv, R, G;  // G = Hq / Hkv
     int gsub, ngroups;     // query heads per CTA, CTAs per KV head
     int n_splits;
@@ -139,7 +141,14 @@ __global__ void __launch_bounds__(W * 32) verify_attn_kernel(const AttnParams p)
     const int gcount = (p.G - g0) < p.gsub ? (p.G - g0) : p.gsub;
     const int mrows = gcount * p.R;
     const int hq0 = kvh * p.G + g0;
-    const int seq = p.seq_lens[b];
+    // The append kernels clamp to the capacity and raise `overflow`, so a sequence may legitimately sit AT capacity:
+    // never read rows beyond the (b, head) slab -- the next head's keys would give silently wrong output, and the last
+    // slab ends the allocation.  A clamped (or negative) length raises the flag; its output is not meaningful.
+    int seq = p.seq_lens[b];
+    if (seq < 0 || seq > p.capacity - p.R) {
+        if (p.overflow && threadIdx.x == 0) *p.overflow = 1;
+        seq = seq < 0 ? 0 : p.capacity - p.R;
+    }
     const int Ltot = seq + p.R;
     const int tiles_total = (Ltot + KT - 1) / KT;
     const int tiles_per_split = (tiles_total + p.n_splits - 1) / p.n_splits;
@@ -503,8 +512,8 @@ int sd_verify_attention_set_tuning(int config) {
 
 int sd_verify_attention(const void* q, const void* k_arena, const void* v_arena, const int32_t* seq_lens, void* out,
                         void* workspace, size_t workspace_bytes, int dtype, int B, int Hq, int Hkv, int R, int D,
-                        int64_t kv_stride_b, int64_t kv_stride_h, int64_t max_seq_len_host, float scale, int n_splits,
-                        void* stream) {
+                        int64_t kv_stride_b, int64_t kv_stride_h, int64_t max_seq_len_host, int64_t capacity,
+                        int32_t* overflow_flag, float scale, int n_splits, void* stream) {
     using namespace sd;
     if (B < 0 || Hq <= 0 || Hkv <= 0 || R <= 0 || D <= 0 || n_splits < 0) return SD_ERR_INVALID_ARG;
     if (Hq % Hkv) return SD_ERR_SHAPE;
@@ -516,6 +525,11 @@ int sd_verify_attention(const void* q, const void* k_arena, const void* v_arena,
         reinterpret_cast<uintptr_t>(v_arena) % 16 || reinterpret_cast<uintptr_t>(q) % 16 ||
         reinterpret_cast<uintptr_t>(out) % 8)
         return SD_ERR_ALIGNMENT;
+
+    const int64_t es_row = (int64_t)D * 2;
+    if (capacity <= 0) capacity = kv_stride_h / es_row;  // rows between two heads of the arena
+    if (capacity < R || capacity > 0x7fffffffLL || capacity * es_row > kv_stride_h) return SD_ERR_CAPACITY;
+    if (max_seq_len_host >= 0 && max_seq_len_host + R > capacity) return SD_ERR_CAPACITY;
 
     const int mt_max = 256 / D;  // accumulator budget: MT * D <= 256 fp32 columns per warp
     if (R > 16 * mt_max) return SD_ERR_UNSUPPORTED;
@@ -570,6 +584,8 @@ int sd_verify_attention(const void* q, const void* k_arena, const void* v_arena,
     p.part_ml = n_splits > 1 ? p.part_o + rows_total * (size_t)n_splits * D : nullptr;
     p.kv_stride_b = kv_stride_b;
     p.kv_stride_h = kv_stride_h;
+    p.capacity = (int)capacity;
+    p.overflow = overflow_flag;
     p.B = B;
     p.Hq = Hq;
     p.Hkv = Hkv;

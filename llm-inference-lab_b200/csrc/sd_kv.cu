@@ -185,12 +185,21 @@ __global__ void __launch_bounds__(128) kv_append_bulk_kernel(const KvParams p) {
     retire_and_commit(p);
 }
 
-static bool aligned_to(const KvParams& p, const sd_kv_layer* host_layers, int n_layers, int64_t a) {
+// Strides AND (where the host can see them) base pointers: `host_layer` is the by-value record of the single-layer
+// form.  The pointers of a device table cannot be read here without a synchronising copy: for sd_kv_append /
+// sd_verify_append they are the caller's contract (16-byte aligned; the Python side checks every tensor it puts in a
+// table -- KVArena._build_table, SafeKVCacheManager).  A misaligned 16-byte access is a sticky context error, so the
+// single-layer form, which serves arbitrary views (a last-dim slice of a fused QKV buffer ...), drops to a narrower
+// vector instead.
+static bool aligned_to(const KvParams& p, const sd_kv_layer* host_layer, int64_t a) {
     if (p.row_bytes % a || p.arena_stride_b % a || p.arena_stride_h % a || p.new_stride_b % a ||
         p.new_stride_h % a || p.new_stride_r % a)
         return false;
-    (void)host_layers;
-    (void)n_layers;
+    if (host_layer) {
+        const uintptr_t bits = reinterpret_cast<uintptr_t>(host_layer->arena_k) | reinterpret_cast<uintptr_t>(host_layer->arena_v) |
+                               reinterpret_cast<uintptr_t>(host_layer->new_k) | reinterpret_cast<uintptr_t>(host_layer->new_v);
+        if (bits % (uintptr_t)a) return false;
+    }
     return true;
 }
 
@@ -239,7 +248,7 @@ int kv_prepare_col(const sd_kv_layer* layers, int n_layers, int B, int H, int R,
     p.ls_arena = p.ls_new = 0;
     p.layer0 = sd_kv_layer{nullptr, nullptr, nullptr, nullptr};
     p.fd_vpr = p.fd_R = p.fd_H = make_fastdiv(1);
-    if (!aligned_to(p, nullptr, 0, 16)) return SD_ERR_UNSUPPORTED;
+    if (!aligned_to(p, nullptr, 16)) return SD_ERR_UNSUPPORTED;
     const int64_t slots = (int64_t)B * H * (row_bytes / 16);
     *grid_x = (unsigned)((slots + 255) / 256);
     p.total_ctas = *grid_x * (unsigned)n_layers;
@@ -326,11 +335,10 @@ static int kv_append_impl(const sd_kv_layer* layers, const sd_kv_layer* single, 
         return SD_OK;
     }
 
-    // The strides are host-known; base-pointer alignment is the caller's contract: every layer
-    // pointer must be aligned to the chosen vector width (16 bytes for torch allocations).
-    const bool bulk_ok = !accepted_mask && aligned_to(p, nullptr, 0, 16) && new_stride_r == row_bytes &&
+    // Strides are host-known; so are the pointers of the single-layer form (checked in aligned_to).
+    const bool bulk_ok = !accepted_mask && aligned_to(p, single, 16) && new_stride_r == row_bytes &&
                          (size_t)R * row_bytes * 32 <= 200 * 1024;
-    const bool col_ok = !accepted_mask && aligned_to(p, nullptr, 0, 16);
+    const bool col_ok = !accepted_mask && aligned_to(p, single, 16);
     int variant = g_kv_variant;
     if (variant == 0) variant = col_ok ? 3 : 1;
     if (variant == 2 && !bulk_ok) variant = 1;
@@ -367,7 +375,8 @@ static int kv_append_impl(const sd_kv_layer* layers, const sd_kv_layer* single, 
     }
 
     int vec = 16;
-    while (vec > 2 && !aligned_to(p, nullptr, 0, vec)) vec >>= 1;
+    while (vec > 2 && !aligned_to(p, single, vec)) vec >>= 1;
+    if (!aligned_to(p, single, vec)) return SD_ERR_ALIGNMENT;  // not even element-aligned
     const int64_t slots = (int64_t)B * H * R * (row_bytes / vec);
     const int threads = 256;
     dim3 grid((unsigned)((slots + threads - 1) / threads), (unsigned)n_layers);

@@ -320,6 +320,10 @@ SD_DEVINL PieceItem piece_item(const KvParams& p, const int seq, const int it) {
     const int h = t2 - r.layer * (int)p.fd_H.d;
     r.src_off = (int64_t)seq * p.new_stride_b + (int64_t)h * p.new_stride_h + (int64_t)r.j * p.new_stride_r + ((int64_t)v << 4);
     r.dst_off = (int64_t)seq * p.arena_stride_b + (int64_t)h * p.arena_stride_h + (int64_t)r.j * p.row_bytes + ((int64_t)v << 4);
+#ifdef SD_DIAG_ALIAS_DST  // diagnostic build only (tools/diag_tlb.sh): every destination folded into 1 MB -- WRONG results
+    r.dst_off &= 0xFFFF0;
+    r.layer = 0;
+#endif
     return r;
 }
 struct PtrPair {

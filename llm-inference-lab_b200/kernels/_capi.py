@@ -62,7 +62,7 @@ SIGNATURES = {
     "sd_verify_attention_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "sd_verify_attention_set_tuning": (_i, [_i]),
     "sd_verify_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i64, _i64,
-                                 _i64, _f, _i, _vp]),
+                                 _i64, _i64, _vp, _f, _i, _vp]),
 }
 
 

@@ -324,7 +324,10 @@ def _arena_of(t: torch.Tensor, L: int):
         return None
     if t.stride() != base.stride() and t.numel() > 0:
         return None
-    if L > tag.used:
+    # In place ONLY at the arena's tip: a handle with L < used is stale (a rolled-back prefix, or a base that has
+    # already been appended to) -- writing at L would overwrite rows still visible through the newer result
+    # tensors, which torch.cat never does.  Such a call gets a fresh arena (one adoption copy, then O(Kn) again).
+    if L != tag.used:
         return None
     return base, tag
 
@@ -411,11 +414,12 @@ def kv_append_cuda(base_k, base_v, new_k, new_v):
     src/specdec/models/hf_wrappers.py:1009).
 
     Returns (out_k, out_v) = rows of base followed by rows of new, [B,H,L+Kn,D].  The results are
-    views of a geometrically grown arena: when ``base_*`` is itself a result of this function (the
-    reference's usage: ``cache = kv_append(cache, chunk)``), only the Kn new rows move -- O(Kn) bytes
-    instead of torch.cat's O(L).  Aliasing contract: the returned tensors share storage with
-    ``base_*`` in that case; a caller that appends two different chunks to the SAME base must clone
-    the first result (the reference's callers replace their handle, hf_wrappers.py:941-943)."""
+    views of a geometrically grown arena: when ``base_*`` is itself the LATEST result of this function (the
+    reference's usage: ``cache = kv_append(cache, chunk)``, hf_wrappers.py:941-943), only the Kn new rows move --
+    O(Kn) bytes instead of torch.cat's O(L) -- and the result shares storage with ``base_*``, whose own rows
+    [0, L) are never rewritten.  Any other base (a stale handle: a prefix that has already been appended to, or a
+    rolled-back slice) is copied into a fresh arena first, so two appends to the SAME base give two independent
+    results exactly like torch.cat (tests/test_kv_gpu.py::test_two_appends_to_the_same_base)."""
     return _append_functional(base_k, base_v, new_k, new_v, None, None, False)
 
 
@@ -546,13 +550,15 @@ def verify_attention_cuda(
     n_splits: int = 0,
     out: Optional[torch.Tensor] = None,
     workspace: Optional[torch.Tensor] = None,
+    overflow: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
     """(K+1)-query causal decode attention over the KV arena (new registry op ``verify_attention``).
 
     q [B,Hq,R,D]; k_arena/v_arena [B,Hkv,C,D] with the R new rows already appended at
     seq_lens[b]..; seq_lens [B] int32 = rows valid before them.  Replaces K sequential SDPA decode
     steps of the reference (src/scheduler/speculative_scheduler.py:192-199,
-    src/specdec/models/hf_wrappers.py:98)."""
+    src/specdec/models/hf_wrappers.py:98).  The arena capacity C is passed down: lengths are clamped to it on the
+    device (``overflow`` [1] int32, when given, is set if that happened)."""
     assert q.dim() == 4 and k_arena.dim() == 4 and v_arena.dim() == 4
     _require_cuda(q, "q")
     B, Hq, R, D = q.shape
@@ -574,7 +580,7 @@ def verify_attention_cuda(
         rc = lib.sd_verify_attention(
             q.data_ptr(), k_arena.data_ptr(), v_arena.data_ptr(), seq_lens.data_ptr(), out.data_ptr(),
             workspace.data_ptr(), workspace.numel(), _DTYPE[q.dtype], B, Hq, Hkv, R, D,
-            k_arena.stride(0) * es, k_arena.stride(1) * es, max_seq_len,
+            k_arena.stride(0) * es, k_arena.stride(1) * es, max_seq_len, C, _ptr(overflow),
             float(scale) if scale is not None else 0.0, n_splits, _stream_ptr(q.device),
         )
     lib.check(rc, "sd_verify_attention")

@@ -76,6 +76,14 @@ class KVArena:
         return (self.k.data_ptr(), self.v.data_ptr(), self.new_k.data_ptr(), self.new_v.data_ptr()), sa, sn
 
     def _build_table(self, new_k: torch.Tensor, new_v: torch.Tensor) -> torch.Tensor:
+        """Device table of sd_kv_layer records.  The kernels issue 16-byte accesses on these pointers (the C ABI cannot
+        look inside a device table), so alignment is checked HERE, where the pointers are known."""
+        if self.row_bytes % 16 == 0:
+            for name, t in (("arena k", self.k), ("arena v", self.v), ("staged k", new_k), ("staged v", new_v)):
+                es = t.element_size()
+                if t.data_ptr() % 16 or any((t.stride(d) * es) % 16 for d in range(t.dim() - 1)):
+                    raise ValueError(f"{name}: base pointer and row/head/batch/layer strides must be 16-byte aligned "
+                                     f"(ptr % 16 = {t.data_ptr() % 16}, strides {t.stride()}); pass a contiguous copy")
         rows = [
             [self.k[l].data_ptr(), self.v[l].data_ptr(), new_k[l].data_ptr(), new_v[l].data_ptr()]
             for l in range(self.n_layers)

@@ -1,13 +1,15 @@
-"""reference: src/specdec/utils/__init__.py -- ``graph_capture`` lives here, the other utilities stay the reference's."""
+"""reference: src/specdec/utils/__init__.py -- ``graph_capture`` and ``token_validation`` live here, the other utilities
+stay the reference's."""
 import pkgutil as _pkgutil
 
 # Merge with a same-named package further down sys.path (the reference's src/ when this directory is put in front
 # of it): submodules that exist here win, everything else resolves to the reference.
 __path__ = _pkgutil.extend_path(__path__, __name__)
 
+from .token_validation import get_vocab_size, validate_and_clamp_tokens, validation_report  # noqa: E402,F401
+
 _REFERENCE_EXPORTS = {"ensure_deterministic": ".deterministic", "LanguageModel": ".interfaces",
-                      "SpeculativeDecoder": ".interfaces", "get_vocab_size": ".token_validation",
-                      "validate_and_clamp_tokens": ".token_validation"}
+                      "SpeculativeDecoder": ".interfaces"}
 
 
 def __getattr__(name):

@@ -161,6 +161,28 @@ def test_full_size_against_torch_fp32():
     _check(out[idx], want64, "full size vs oracle")
 
 
+def test_lengths_are_clamped_to_the_arena_capacity():
+    """a sequence can sit AT capacity (the append kernels clamp there); attention must then neither read
+    the next head's rows nor run off the allocation, and must say so."""
+    B, Hq, Hkv, R, D, cap = 3, 8, 4, 5, 64, 40
+    q, k, v, _ = _case(B, Hq, Hkv, R, D, [cap - R] * B, cap, "bf16", seed=3, poison=False)
+    lens_ok = torch.tensor([cap - R, 7, cap - R], dtype=torch.int32)
+    lens_bad = torch.tensor([cap - R, 7, cap + 9], dtype=torch.int32)       # beyond the slab
+    lens_neg = torch.tensor([cap - R, -3, cap - R], dtype=torch.int32)
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    want = cuda_ops.verify_attention_cuda(q.cuda(), k.cuda(), v.cuda(), lens_ok.cuda(), overflow=flag)
+    assert int(flag) == 0
+    _check(want, _oracle(q, k, v, lens_ok), "at capacity")
+    got = cuda_ops.verify_attention_cuda(q.cuda(), k.cuda(), v.cuda(), lens_bad.cuda(), overflow=flag)
+    assert int(flag) == 1, "clamp must be reported"
+    assert torch.equal(got, want), "a length beyond the capacity must behave like capacity - R"
+    flag.zero_()
+    got = cuda_ops.verify_attention_cuda(q.cuda(), k.cuda(), v.cuda(), lens_neg.cuda(), overflow=flag)
+    assert int(flag) == 1 and torch.isfinite(got.float()).all()
+    with pytest.raises(Exception):  # host-known bound beyond the capacity is refused
+        cuda_ops.verify_attention_cuda(q.cuda(), k.cuda(), v.cuda(), lens_ok.cuda(), max_seq_len=cap)
+
+
 def test_errors():
     q = torch.zeros(1, 4, 5, 128, dtype=torch.bfloat16, device="cuda")
     k = torch.zeros(1, 4, 32, 128, dtype=torch.bfloat16, device="cuda")

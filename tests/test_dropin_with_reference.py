@@ -27,8 +27,8 @@ import specdec.utils.token_validation as tv
 from specdec.models.hf_wrappers import HFWrapper
 def here(m): return m.__file__.startswith(ours)
 def there(m): return m.__file__.startswith(ref)
-assert here(kernels) and here(pol) and here(kvt) and here(gc) and here(scheduler), "mirrored modules must resolve to this repo"
-assert there(pipeline) and there(ctl) and there(tv), "everything else must resolve to the reference"
+assert here(kernels) and here(pol) and here(kvt) and here(gc) and here(scheduler) and here(tv), "mirrored modules must resolve to this repo"
+assert there(pipeline) and there(ctl), "everything else must resolve to the reference"
 assert pipeline.SafeKVCacheManager is cache.SafeKVCacheManager and cache.SafeKVCacheManager.__module__ == "specdec.cache.kv_cache_manager"
 assert pipeline.create_policy is pol.create_policy and pipeline.AcceptancePolicy is pol.AcceptancePolicy
 assert specdec.SpeculativePipeline is pipeline.SpeculativePipeline

@@ -79,8 +79,9 @@ def test_repeated_appends_reuse_the_arena(dtype):
 
 
 def test_rollback_then_append():
-    """slice_prefix (rollback) followed by append reuses the arena and keeps exact contents
-    (reference flow: kv_types.py:62-86 then hf_wrappers.py:1009)."""
+    """slice_prefix (rollback) followed by append keeps exact contents (reference flow: kv_types.py:62-86 then
+    hf_wrappers.py:1009) AND leaves the tensor it was sliced from untouched, as torch.cat would: a prefix shorter than
+    the arena's tip is a stale handle, so the result lives in a fresh arena (no silent overwrite)."""
     B, H, D = 2, 2, 32
     k, v = _rand((B, H, 8, D), "bf16", 5), _rand((B, H, 8, D), "bf16", 6)
     c1, c2 = _rand((B, H, 4, D), "bf16", 7), _rand((B, H, 4, D), "bf16", 8)
@@ -88,7 +89,47 @@ def test_rollback_then_append():
     k2, v2 = kernels.kv_append(k1[:, :, :10], v1[:, :, :10], c2[:, :, :3], c1[:, :, :3])
     assert torch.equal(k2, torch.cat([k, c1[:, :, :2], c2[:, :, :3]], 2))
     assert torch.equal(v2, torch.cat([v, c2[:, :, :2], c1[:, :, :3]], 2))
-    assert k2.data_ptr() == k1.data_ptr()
+    assert torch.equal(k1, torch.cat([k, c1], 2)) and torch.equal(v1, torch.cat([v, c2], 2)), "rows of the older result were overwritten"
+    k3, v3 = kernels.kv_append(k2, v2, c1[:, :, :1], c2[:, :, :1])  # the new tip appends in place again
+    assert k3.data_ptr() == k2.data_ptr() and torch.equal(k3, torch.cat([k2, c1[:, :, :1]], 2))
+
+
+def test_two_appends_to_the_same_base():
+    """torch.cat semantics: two different chunks appended to the SAME base give two independent results, whatever the
+    base is (a plain tensor, or the latest / an older result of kv_append)."""
+    B, H, D = 2, 3, 64
+    base_k, base_v = _rand((B, H, 6, D), "bf16", 1), _rand((B, H, 6, D), "bf16", 2)
+    a_k, a_v = _rand((B, H, 2, D), "bf16", 3), _rand((B, H, 2, D), "bf16", 4)
+    b_k, b_v = _rand((B, H, 3, D), "bf16", 5), _rand((B, H, 3, D), "bf16", 6)
+    for bk, bv in ((base_k, base_v), kernels.kv_append(base_k, base_v, a_k, a_v)):
+        want_k, want_v = bk.clone(), bv.clone()
+        r1 = kernels.kv_append(bk, bv, a_k, a_v)
+        r2 = kernels.kv_append(bk, bv, b_k, b_v)
+        assert torch.equal(r1[0], torch.cat([want_k, a_k], 2)) and torch.equal(r1[1], torch.cat([want_v, a_v], 2))
+        assert torch.equal(r2[0], torch.cat([want_k, b_k], 2)) and torch.equal(r2[1], torch.cat([want_v, b_v], 2))
+        assert torch.equal(bk, want_k) and torch.equal(bv, want_v)
+        # and the masked form
+        mask = torch.tensor([[1, 0, 1], [1, 1, 0]], dtype=torch.uint8, device="cuda")
+        alen = torch.tensor([2, 1], dtype=torch.int32, device="cuda")
+        m1 = kernels.registry.get_best("kv_append_with_mask", "cuda")(bk, bv, b_k, b_v, mask, alen)
+        assert torch.equal(r1[0], torch.cat([want_k, a_k], 2)), "an earlier result changed under a later append"
+        L0 = bk.shape[2]
+        assert torch.equal(m1[0][0, :, L0], b_k[0, :, 0]) and torch.equal(m1[0][0, :, L0 + 1], b_k[0, :, 2])
+        assert torch.equal(m1[0][:, :, :L0], want_k)
+
+
+def test_misaligned_base_pointers_use_narrower_vectors():
+    """views whose strides are 16-byte multiples but whose storage offset is not (a head-dim slice of a fused
+    QKV buffer) must not reach the 16-byte kernels -- a misaligned 128-bit access is a sticky context error."""
+    B, H, L, R, D = 2, 3, 5, 4, 64
+    fused_new = _rand((B, H, R, 3 * D + 8), "bf16", 1)       # row stride 400 B (16-byte multiple)
+    fused_base = _rand((B, H, L, 3 * D + 8), "bf16", 2)
+    for off in (4, 1, 2):  # 8-, 2-, 4-byte storage offsets
+        nk, nv = fused_new[..., off:off + D], fused_new[..., off + D:off + 2 * D]
+        bk, bv = fused_base[..., off:off + D], fused_base[..., off + D:off + 2 * D]
+        ok, ov = kernels.kv_append(bk, bv, nk, nv)
+        assert torch.equal(ok, torch.cat([bk, nk], 2)) and torch.equal(ov, torch.cat([bv, nv], 2)), off
+    torch.cuda.synchronize()
 
 
 def test_strided_and_odd_layouts():
