@@ -77,6 +77,7 @@ def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-time", action="store_true")
     ap.add_argument("--quick", action="store_true", help="a handful of bf16 cases only")
+    ap.add_argument("--time-only", action="store_true")
     a = ap.parse_args()
     build()
     f = load()
@@ -92,6 +93,8 @@ def main() -> int:
                  for (T, k, p_) in ((0.7, 50, 0.9), (None, None, None), (1.0, None, 0.9))]
     bad = 0
     ran = 0
+    if a.time_only:
+        cases = []
     for ci, (dtype, B, V, kind, T, k, p_) in enumerate(cases):
         if k is not None and k >= V:
             continue
@@ -143,6 +146,8 @@ def main() -> int:
     res = {"product_us": timed(lambda i: cuda_ops.sample_bonus_cuda(sets[i % 4], row_index=row_index, uniform=uniform,
                                                                     temperature=0.7, top_k=50, top_p=0.9, out=out))}
     for cluster in (2, 4, 8):
+        if not fits(V, cluster, torch.bfloat16):
+            continue
         res[f"cluster{cluster}_us"] = timed(lambda i: cluster_sample(f, sets[i % 4], row_index, uniform, 0.7, 50, 0.9, cluster, out, kept))
     res["row_bytes_total"] = B * V * 2
     print(json.dumps(res), flush=True)

@@ -442,7 +442,8 @@ int sd_sample_bonus(const void* logits, int logit_dtype, int64_t stride_b, int64
                     int32_t* kept_count, int B, int rows, int V, void* stream);
 
 /* Tile configuration of the attention kernel (evidence runs): 0 = heuristic, 1 = 16-key tiles x 3
- * stages (two CTAs per SM at D = 128), 2 = 32-key tiles x 3 (4 at D = 64) stages, 3 = 32-key x 2. */
+ * stages (two CTAs per SM at D = 128), 2 = 32-key tiles x 3 (4 at D = 64) stages, 3 = 32-key x 2; D = 64 only:
+ * 4 / 5 / 6 = 16-key tiles x 3 / 4 / 6 stages (measured slower than the default, csrc/sd_attn.cu). */
 int sd_verify_attention_set_tuning(int config);
 
 #ifdef __cplusplus

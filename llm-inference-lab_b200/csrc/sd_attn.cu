@@ -466,16 +466,26 @@ static cudaError_t launch_attn(const AttnParams& p, dim3 grid, int config, cudaS
     } else {
         if (config == 2) return launch_attn_cfg<T, D, MT, 32, 4>(p, grid, st);
         if (config == 3) return launch_attn_cfg<T, D, MT, 32, 2>(p, grid, st);
+        // 16-key tiles (evidence runs): half the ring per CTA.  Measured on B200 (tools/sweep_attention.py, Llama-3.2-1B,
+        // B = 64, L = 1024): 32.2 us against 30.1 us for the default -- the kernel is limited to two CTAs per SM by its
+        // 172 registers, not by shared memory, and forcing 128 registers (four CTAs: the whole 512-CTA grid resident)
+        // spills into the main loop (41.6 us).
+        if (config == 4) return launch_attn_cfg<T, D, MT, 16, 3>(p, grid, st);
+        if (config == 5) return launch_attn_cfg<T, D, MT, 16, 4>(p, grid, st);
+        if (config == 6) return launch_attn_cfg<T, D, MT, 16, 6>(p, grid, st);
         return launch_attn_cfg<T, D, MT, 32, 3>(p, grid, st);
     }
 }
 
-static int attn_tile_keys(int D, int config) { return (D == 128 && (config == 0 || config == 1)) ? 16 : 32; }
+static int attn_tile_keys(int D, int config) {
+    if (D == 128) return (config == 0 || config == 1) ? 16 : 32;
+    return config >= 4 ? 16 : 32;
+}
 static int attn_ctas_per_sm(int D, int MT, int config) {
     // shared-memory bound (227 KB per SM, 1 KB reserved per CTA)
     int bytes;
     if (D == 128) bytes = config == 2 ? 196608 : config == 3 ? 131072 : 98304;
-    else bytes = config == 2 ? 131072 : config == 3 ? 65536 : 98304;
+    else bytes = config == 2 ? 131072 : config == 3 ? 65536 : config == 4 ? 49152 : config == 5 ? 65536 : config == 6 ? 98304 : 98304;
     bytes += MT * 16 * D * 2 + 1024;
     int n = (227 * 1024) / bytes;
     return n < 1 ? 1 : n;
@@ -505,7 +515,7 @@ size_t sd_verify_attention_workspace_bytes(int B, int Hq, int R, int D, int max_
 }
 
 int sd_verify_attention_set_tuning(int config) {
-    if (config < 0 || config > 3) return SD_ERR_INVALID_ARG;
+    if (config < 0 || config > 6) return SD_ERR_INVALID_ARG;  // 4..6: 16-key tiles at D = 64 (D = 128 treats them as 0)
     sd::g_attn_tuning.config = config;
     return SD_OK;
 }
