@@ -117,6 +117,80 @@ def build_cuda_kernels(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+# ---- the torch shim (csrc_torch/sd_torch_ops.cpp): host code only, g++ against the torch headers ------------------------
+TORCH_SHIM_SRC = PKG_ROOT / "csrc_torch" / "sd_torch_ops.cpp"
+TORCH_SHIM_PATH = LIB_DIR / "sd_b200_torch.so"
+TORCH_SHIM_HASH = LIB_DIR / "sd_b200_torch.hash"
+
+
+def _shim_hash() -> str:
+    import torch
+
+    h = hashlib.sha256()
+    h.update(TORCH_SHIM_SRC.read_bytes())
+    h.update((INCLUDE / "sd_verify.h").read_bytes())
+    h.update(torch.__version__.encode())
+    return h.hexdigest()
+
+
+def build_torch_shim(force: bool = False) -> Path:
+    """Compile the torch-side shim (argument marshalling + TORCH_LIBRARY registration; no kernels) and link it against
+    libsd_verify_b200.so.  Ahead of time, in tree, hash-cached like the CUDA library: nothing is JIT-compiled at run
+    time (a JIT cache under ~/.cache would not travel to the GPU box)."""
+    force = force or os.environ.get("SD_B200_REBUILD", "0") == "1"
+    if not force and TORCH_SHIM_PATH.exists() and TORCH_SHIM_HASH.exists() and TORCH_SHIM_HASH.read_text().strip() == _shim_hash():
+        return TORCH_SHIM_PATH
+    gxx = shutil.which("g++")
+    if gxx is None:
+        if TORCH_SHIM_PATH.exists():
+            logger.warning("g++ not found; using the prebuilt %s (hash not verified)", TORCH_SHIM_PATH)
+            return TORCH_SHIM_PATH
+        raise RuntimeError("g++ not found and no prebuilt sd_b200_torch.so is present")
+    import sysconfig
+
+    import torch
+    from torch.utils import cpp_extension as ce
+
+    build_cuda_kernels()
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    inc = [str(INCLUDE), *ce.include_paths(), sysconfig.get_paths()["include"], os.path.join(cuda_home, "include")]
+    libdirs = [str(LIB_DIR), *ce.library_paths(), os.path.join(cuda_home, "lib64")]
+    cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=sd_b200_torch", "-DTORCH_API_INCLUDE_EXTENSION_H",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
+    for i in inc:
+        cmd += ["-I", i]
+    cmd += [str(TORCH_SHIM_SRC), "-o", str(TORCH_SHIM_PATH)]
+    for d in libdirs:
+        cmd += ["-L", d]
+    cmd += ["-lsd_verify_b200", "-ltorch", "-ltorch_cpu", "-ltorch_python", "-lc10", "-lc10_cuda", "-lcudart", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed for {TORCH_SHIM_SRC.name}:\n{r.stdout[-2000:]}\n{r.stderr[-6000:]}")
+    TORCH_SHIM_HASH.write_text(_shim_hash())
+    logger.info("built %s", TORCH_SHIM_PATH)
+    return TORCH_SHIM_PATH
+
+
+_SHIM = None
+
+
+def load_torch_shim():
+    """Import lib/sd_b200_torch.so (builds it when stale).  Importing it registers sd_b200::verify_prefix,
+    sd_b200::verify_prefix_bonus and sd_b200::kv_append_rows_ with the torch dispatcher (CUDA key only)."""
+    global _SHIM
+    if _SHIM is None:
+        import ctypes
+        import importlib.util
+
+        path = build_torch_shim()
+        ctypes.CDLL(str(build_cuda_kernels()), mode=ctypes.RTLD_GLOBAL)  # (also found through the shim's rpath)
+        spec = importlib.util.spec_from_file_location("sd_b200_torch", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _SHIM = mod
+    return _SHIM
+
+
 def load_kernels():
     """Build if needed and return the loaded C-ABI binding (kernels._capi.Lib).
 

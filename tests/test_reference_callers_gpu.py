@@ -120,8 +120,8 @@ for dtype in (torch.float16, torch.bfloat16, torch.float32):
     assert got.seq_len == want.seq_len == sum(sizes)
     for (gk, gv), (wk, wv) in zip(got.past_key_values, want.past_key_values):
         assert torch.equal(gk, wk) and torch.equal(gv, wv)
-        base = gk._base
-        assert base is not None and hasattr(base, "_sd_arena"), "result did not come from the sd_b200 kv_append (fallback taken?)"
+        info = kernels.cuda_ops.arena_info(gk)
+        assert info is not None and info[0] == sum(sizes), "result did not come from the sd_b200 kv_append (fallback taken?)"
 print("ok")
 ''')
 
