@@ -422,8 +422,9 @@ int sd_verify_attention(const void* q, const void* k_arena, const void* v_arena,
  * Replaces  sample_bonus_token_from_logits(logits[V], temperature, do_sample, top_p, top_k)
  *           reference: src/specdec/core/pipeline.py:48-147, called once per sequence at
  *           :3140-3163 / :3174-3206 / :3341-3362 on logits row accept_len[b].
- * for the whole batch in one launch (one CTA per sequence, no sort: radix select by count for top-k
- * and by probability mass for top-p, fixed-point masses -> deterministic).
+ * for the whole batch in one launch (one CTA per sequence, no sort of the vocabulary: with 0 < top_k <= 1024 two
+ * passes over the row collect a superset of the top-k, which is finished in shared memory; otherwise radix select by
+ * count for top-k and by probability mass for top-p; fixed-point masses -> deterministic).
  *
  * logits     [B, rows, V], element strides (stride_b, stride_r, 1)
  * row_index  [B] int32 (nullable): row = clamp(row_index[b] + row_bias, 0, rows-1); NULL -> row_const.
@@ -440,6 +441,12 @@ int sd_sample_bonus(const void* logits, int logit_dtype, int64_t stride_b, int64
                     const int32_t* row_index, int row_bias, int row_const, const float* uniform,
                     float temperature, int top_k, float top_p, int32_t* out_tokens,
                     int32_t* kept_count, int B, int rows, int V, void* stream);
+
+/* Bonus sampler: 1 (default) = requests with 0 < top_k <= 1024 take the two-pass candidate path (the k-th largest
+ * per-thread maximum bounds the threshold, one more pass collects the superset, sorts in shared memory finish the
+ * job) and fall back to the general radix-select path only when the superset does not fit; 0 = always the general
+ * path.  Both give the same token (tests/test_sample_gpu.py compares them). */
+int sd_sample_set_fast_path(int enabled);
 
 /* Tile configuration of the attention kernel (evidence runs): 0 = heuristic, 1 = 16-key tiles x 3
  * stages (two CTAs per SM at D = 128), 2 = 32-key tiles x 3 (4 at D = 64) stages, 3 = 32-key x 2; D = 64 only:

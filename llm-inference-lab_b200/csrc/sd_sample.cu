@@ -19,6 +19,8 @@
 
 namespace sd {
 
+static int g_sample_no_fast = 0;  // evidence runs / tests: 1 = always the general (radix-select) path
+
 template <typename T>
 __global__ void __launch_bounds__(kSampThreads) sample_bonus_kernel(const SampleParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -59,23 +61,14 @@ __global__ void __launch_bounds__(kSampThreads) sample_bonus_kernel(const Sample
     // ---- pass A: maximum (order key) and its first index ----
     uint32_t kmax = 0u;
     int amax = 0x7fffffff;
-    for (int tb = 0; tb < V; tb += kTile * kBatch) {
-        float xs[kBatch][8];
-        bool ok[kBatch][8];
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) G.load8(tb + q * kTile + tid * 8, xs[q], ok[q]);
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const uint32_t k = order_key(xs[q][e]);
-                if (ok[q][e] && k > kmax) {  // strictly greater: indices ascend within a thread, the first one wins
-                    kmax = k;
-                    amax = tb + q * kTile + tid * 8 + e;
-                }
-            }
+    scan_row<8>(G, [&](int idx, float x) {
+        const uint32_t k = order_key(x);
+        if (k > kmax) {  // strictly greater: indices ascend within a thread, the first one wins
+            kmax = k;
+            amax = idx;
         }
-    }
+    });
+    const uint32_t my_max = kmax;  // this thread's own maximum (the fast top-k path bounds the threshold with these)
     {
         const uint32_t wk = __reduce_max_sync(0xffffffffu, kmax);
         const unsigned wp = __reduce_min_sync(0xffffffffu, kmax == wk ? (unsigned)amax : 0x7fffffffu);
@@ -116,6 +109,16 @@ __global__ void __launch_bounds__(kSampThreads) sample_bonus_kernel(const Sample
     bool has_sel = false;
     uint32_t token = 0xffffffffu;
     unsigned kept = 0;
+    if (p.top_k > 0 && p.top_k < V && p.top_k <= kCompactCap && !p.no_fast_path) {
+        // two-pass path on <= 1024 candidates; the histogram scratch is free here and holds its three lists
+        if (topk_fast_path(G, sh, p, m, u, my_max, reinterpret_cast<unsigned long long*>(smem_raw), token, kept)) {
+            if (tid == 0) {
+                p.out[b] = token == 0xffffffffu ? amax : (int)token;
+                if (p.kept_count) p.kept_count[b] = (int)kept;
+            }
+            return;
+        }
+    }
     if (p.top_k > 0 && p.top_k < V) {
         sel = radix_select(G, sh, p, m, false, (unsigned)p.top_k, 0ull, sel, false);
         has_sel = true;
@@ -167,6 +170,11 @@ __global__ void __launch_bounds__(kSampThreads) sample_bonus_kernel(const Sample
 
 extern "C" {
 
+int sd_sample_set_fast_path(int enabled) {
+    sd::g_sample_no_fast = enabled ? 0 : 1;
+    return SD_OK;
+}
+
 int sd_sample_bonus(const void* logits, int logit_dtype, int64_t stride_b, int64_t stride_r, const int32_t* row_index,
                     int row_bias, int row_const, const float* uniform, float temperature, int top_k, float top_p,
                     int32_t* out_tokens, int32_t* kept_count, int B, int rows, int V, void* stream) {
@@ -193,6 +201,7 @@ int sd_sample_bonus(const void* logits, int logit_dtype, int64_t stride_b, int64
     p.top_p = top_p > 0.f ? top_p : 1.0f;
     p.out = out_tokens;
     p.kept_count = kept_count;
+    p.no_fast_path = sd::g_sample_no_fast;
     // digits that cover every information bit of the order key: fp32 32, fp16 19 (1+8+10 after widening), bf16 16
     p.ndigits = logit_dtype == SD_F32 ? 4 : (logit_dtype == SD_F16 ? 3 : 2);
     const size_t smem = (size_t)kSampWarps * kBins * (4 + 8) + (size_t)kCompactCap * 8;

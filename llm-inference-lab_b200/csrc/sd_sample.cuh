@@ -25,6 +25,7 @@ struct SampleParams {
     int32_t* out;
     int32_t* kept_count;       // nullable: size of the final candidate set (diagnostics / tests)
     int ndigits;               // radix passes of 8 bits: bf16 2, fp16 3, fp32 4
+    int no_fast_path;          // 1 = skip topk_fast_path (tests compare both paths)
 };
 
 struct SelectResult {
@@ -414,5 +415,168 @@ SD_DEVINL void nucleus_and_draw(const Row& R, const SampShared& sh, const Sample
 }
 
 constexpr int kCompactCap = 1024;  // top-k values up to this size continue on a compacted candidate list in smem
+
+// ---- fast path for 0 < top_k <= kCompactCap: two passes over the row, everything else on <= 1024 candidates --------
+// The general path above finds the top-k threshold with an 8-bit radix select over the WHOLE row (one pass per digit,
+// a warp-wide match per element), compacts the survivors in index order (a block scan per tile) and runs the by-mass
+// select on them: ~4 row passes and a dozen 256-bucket walks, 157 us at B = 64, V = 128256.  Here:
+//   1. the k-th largest of the 1024 PER-THREAD maxima (already computed by the maximum pass) is a lower bound of the
+//      k-th largest element of the row, so {key >= that bound} is a superset of the top-k -- for a row that is not
+//      adversarially ordered a few elements more than k;
+//   2. ONE more pass over the row (L2-resident) collects that superset, unordered, into shared memory; more than
+//      kCompactCap of them (a sorted or near-constant row) -> return false, the general path takes over;
+//   3. a bitonic sort by (key descending, index ascending) makes the first k entries exactly the reference's top-k
+//      (ties at the threshold: lowest indices first, as a stable descending sort); top-p is a prefix of that list
+//      (inclusive cumulative fixed-point mass <= top_p * Z, at least one: pipeline.py:105-121); the draw walks the kept
+//      entries in INDEX order (second sort) -- the same integers as the general path, hence the same token.
+// One pass over a row in global memory with NB 16-byte loads in flight per thread (raw vectors: 4 registers per 8
+// sixteen-bit elements), visiting every element as f(index, value) -- per thread in ASCENDING index order.  A CTA owns a
+// whole SM here, so memory-level parallelism is per thread: with the two 8-float batches of load8 a 256 KB row costs
+// eight dependent HBM round trips (~25 us per pass); with 8 vectors in flight it is two.
+template <int NB, typename T, typename F>
+SD_DEVINL void scan_row(const GlobalRow<T>& G, F&& f) {
+    const int tid = threadIdx.x, n = G.n;
+    if constexpr (sizeof(T) == 2) {
+        if ((reinterpret_cast<uintptr_t>(G.row) & 15u) == 0) {
+            const int nvec = n >> 3;
+            const uint4* vp = reinterpret_cast<const uint4*>(G.row);
+            for (int v0 = 0; v0 < nvec; v0 += kSampThreads * NB) {
+                uint4 v[NB];
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    const int vi = v0 + q * kSampThreads + tid;
+                    v[q] = vi < nvec ? ldg_stream_v4(vp + vi) : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int q = 0; q < NB; ++q) pin_loaded(v[q]);
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    const int vi = v0 + q * kSampThreads + tid;
+                    if (vi < nvec) {
+                        const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                                f(vi * 8 + 2 * h, __uint_as_float(w[h] << 16));
+                                f(vi * 8 + 2 * h + 1, __uint_as_float(w[h] & 0xffff0000u));
+                            } else {
+                                const float2 x2 = __half22float2(*reinterpret_cast<const __half2*>(&w[h]));
+                                f(vi * 8 + 2 * h, x2.x);
+                                f(vi * 8 + 2 * h + 1, x2.y);
+                            }
+                        }
+                    }
+                }
+            }
+            const int t = nvec * 8 + tid;  // < 8 elements left
+            if (t < n) f(t, to_float<T>(G.row[t]));
+            return;
+        }
+    }
+    for (int tb = 0; tb < n; tb += kTile * kBatch) {
+        float xs[kBatch][8];
+        bool ok[kBatch][8];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) G.load8(tb + q * kTile + tid * 8, xs[q], ok[q]);
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (ok[q][e]) f(tb + q * kTile + tid * 8 + e, xs[q][e]);
+        }
+    }
+}
+
+// descending bitonic sort of the first `size` entries (a power of two <= 1024); called by all 1024 threads
+SD_DEVINL void bitonic_sort_desc(unsigned long long* a, const int size) {
+    const int i = threadIdx.x;
+    for (int k = 2; k <= size; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int ixj = i ^ j;
+            if (ixj > i && ixj < size) {
+                const unsigned long long x = a[i], y = a[ixj];
+                const bool desc = (i & k) == 0;
+                if (desc ? (x < y) : (x > y)) {
+                    a[i] = y;
+                    a[ixj] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Returns false (uniformly) when the candidate superset does not fit: nothing has been written, the caller continues
+// with the general path.  `my_max` = this thread's maximum order key from the maximum pass (0 if it saw no element).
+template <typename T>
+SD_DEVINL bool topk_fast_path(const GlobalRow<T>& R, const SampShared& sh, const SampleParams& p, float m, float u, uint32_t my_max,
+                              unsigned long long* buf /* 3 x 1024 u64 of shared memory */, uint32_t& token_out, unsigned& kept_out) {
+    const int tid = threadIdx.x;
+    const int k = p.top_k;
+    unsigned long long* A = buf;             // sort scratch / candidate list
+    unsigned long long* W = buf + 1024;      // masses of the sorted candidates
+    unsigned long long* I = buf + 2048;      // index-order list of the kept candidates
+    // 1. lower bound of the k-th largest key: the k-th largest per-thread maximum, found bit by bit (the largest t with
+    //    at least k thread maxima >= t: 32 counting barriers instead of a 55-stage sort of 1024 keys)
+    uint32_t tau0 = 0u;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = tau0 | (1u << bit);
+        if (__syncthreads_count(my_max >= cand) >= k) tau0 = cand;
+    }
+    // 2. collect {key >= tau0}
+    if (tid == 0) sh.s_u32[2] = 0u;
+    __syncthreads();
+    scan_row<8>(R, [&](int idx, float x) {
+        const uint32_t key = order_key(x);
+        if (key >= tau0) {
+            const unsigned pos = atomicAdd(&sh.s_u32[2], 1u);
+            if (pos < (unsigned)kCompactCap) W[pos] = ((unsigned long long)key << 32) | (uint32_t)(~(uint32_t)idx);
+        }
+    });
+    __syncthreads();
+    const unsigned c = sh.s_u32[2];
+    __syncthreads();
+    if (c > (unsigned)kCompactCap) return false;
+    // 3. exact order: key descending, index ascending
+    int size = 32;
+    while (size < (int)c) size <<= 1;  // the sorts run on the next power of two, not on all 1024 slots
+    A[tid] = tid < (int)c ? W[tid] : 0ull;
+    __syncthreads();
+    bitonic_sort_desc(A, size);
+    const int nk = k < (int)c ? k : (int)c;  // (c >= k whenever k < V)
+    const unsigned long long ent = A[tid];
+    const uint32_t my_idx = ~(uint32_t)ent;
+    const unsigned long long w = tid < nk ? fixed_mass(key_to_float((uint32_t)(ent >> 32)), m, p.inv_t_log2) : 0ull;
+    int n_kept = nk;
+    if (p.top_p < 1.0f) {
+        ScanPair total;
+        const ScanPair ex = block_exclusive_scan(ScanPair{w, 0u}, total, sh.s_mass, sh.s_cnt);
+        // cumulative probability <= top_p  <=>  cumulative mass <= top_p * Z1 (same integers as nucleus_and_draw)
+        const unsigned long long target = (unsigned long long)((double)p.top_p * (double)total.mass);
+        const unsigned ok = (tid < nk && ex.mass + w <= target) ? 1u : 0u;
+        ScanPair tot2;
+        block_exclusive_scan(ScanPair{0ull, ok}, tot2, sh.s_mass, sh.s_cnt);
+        n_kept = tot2.cnt > 0u ? (int)tot2.cnt : 1;  // "keep at least one token" (pipeline.py:115)
+    }
+    const bool kept = tid < n_kept;
+    W[tid] = kept ? w : 0ull;
+    I[tid] = kept ? (((unsigned long long)(uint32_t)(~my_idx)) << 32) | (unsigned)tid : 0ull;  // descending ~idx == ascending idx
+    __syncthreads();
+    bitonic_sort_desc(I, size);
+    const unsigned long long ie = I[tid];
+    const unsigned long long wj = tid < n_kept ? W[(unsigned)ie & 1023u] : 0ull;
+    ScanPair totz;
+    const ScanPair exz = block_exclusive_scan(ScanPair{wj, 0u}, totz, sh.s_mass, sh.s_cnt);
+    u = u < 0.f ? 0.f : (u > 0.99999994f ? 0.99999994f : u);
+    const unsigned long long target = (unsigned long long)((double)u * (double)totz.mass);
+    if (tid == 0) sh.s_u32[0] = 0xffffffffu;
+    __syncthreads();
+    if (wj && exz.mass <= target && target < exz.mass + wj) sh.s_u32[0] = ~(uint32_t)(ie >> 32);
+    __syncthreads();
+    token_out = sh.s_u32[0];
+    kept_out = (unsigned)n_kept;
+    __syncthreads();
+    return true;
+}
 
 }  // namespace sd

@@ -749,6 +749,11 @@ def device_error(clear: bool = True) -> int:
     return int(v.value)
 
 
+def set_sample_fast_path(enabled: bool = True) -> None:
+    """Bonus sampler: two-pass candidate path for 0 < top_k <= 1024 (default on); off = always the radix-select path."""
+    _capi.lib().check(_capi.lib().sd_sample_set_fast_path(int(enabled)), "sd_sample_set_fast_path")
+
+
 def set_pdl(enabled: bool = True) -> None:
     _capi.lib().check(_capi.lib().sd_set_pdl(int(enabled)), "sd_set_pdl")
 

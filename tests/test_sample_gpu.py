@@ -126,3 +126,38 @@ def test_empirical_distribution_matches_the_filtered_softmax():
     freq = np.bincount(tok, minlength=V) / n
     assert (freq[pr == 0] == 0).all()
     assert np.abs(freq - pr).max() < 4 * np.sqrt(pr.max() / n) + 1e-3
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16", "fp32"])
+@pytest.mark.parametrize("kind", ["randn", "ties", "flat", "peaked", "sorted"])
+def test_fast_topk_path_equals_general_path(dtype, kind):
+    """0 < top_k <= 1024 takes the two-pass candidate path (sd_sample.cuh::topk_fast_path); it must return the token
+    and the kept-set size of the general radix-select path bit for bit -- random rows, rows made of a few distinct
+    values (ties at the threshold, ranked by index), constant rows (everything ties: the candidate superset does not
+    fit, i.e. the fallback), one dominant logit, and a descending row (all top elements in ONE thread)."""
+    for (B, V) in ((16, 128256), (7, 50257), (5, 1000), (3, 37)):
+        g = torch.Generator().manual_seed(V + len(kind))
+        x = torch.randn(B, 3, V, generator=g) * 3.0
+        if kind == "ties":
+            x = torch.round(x * 2.0) / 2.0
+        elif kind == "flat":
+            x = torch.zeros_like(x)
+        elif kind == "peaked":
+            x[:, :, 7 % V] += 40.0
+        elif kind == "sorted":
+            x = torch.sort(x, dim=-1, descending=True).values
+        logits = x.to(TORCH_DT[dtype]).cuda()
+        row_index = torch.randint(0, 3, (B,), generator=g).to(torch.int32).cuda()
+        u = torch.rand(B, generator=g).cuda()
+        for (T, k, p_) in ((0.7, 50, 0.9), (1.0, 1, 1.0), (1.3, 1024, 0.5), (0.7, 17, 1.0), (0.5, 5, 1e-6), (1.0, 200, 0.99)):
+            if k >= V:
+                continue
+            res = []
+            for fast in (True, False):
+                cuda_ops.set_sample_fast_path(fast)
+                tok = torch.full((B,), -7, dtype=torch.int32, device="cuda")
+                kept = torch.full((B,), -7, dtype=torch.int32, device="cuda")
+                cuda_ops.sample_bonus_cuda(logits, row_index=row_index, uniform=u, temperature=T, top_k=k, top_p=p_, out=tok, kept_count=kept)
+                res.append((tok.cpu().tolist(), kept.cpu().tolist()))
+            cuda_ops.set_sample_fast_path(True)
+            assert res[0] == res[1], (dtype, kind, V, T, k, p_)
