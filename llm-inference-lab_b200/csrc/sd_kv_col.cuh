@@ -521,10 +521,16 @@ SD_DEVINL void kv_piece_prefetch(const KvParams& p, const int seq, const int pie
 // the CTA (no dependence on the word).  Tail CTA 0 also serves the multi-GPU exchange.  The last tail CTA to retire
 // closes the launch: once every sequence word is published -- i.e. every verify CTA has published its partial,
 // before which it has consumed the epoch -- it advances the launch epoch.
-SD_DEVINL void kv_tail_body(const KvParams& p, const int t, unsigned long long* trace, uint4* park, const int park_items) {
-    const int seq = p.B - 1 - t / p.tail_pieces, tp = t % p.tail_pieces;
+SD_DEVINL void kv_tail_body(const KvParams& p, int t, unsigned long long* trace, uint4* park, const int park_items) {
     const unsigned tag = step_tag(p.epoch_word);
-    {
+    // With a multi-GPU exchange the FIRST tail CTA carries no rows: it is dispatched as soon as a verify CTA retires,
+    // polls the records while they arrive and is done one NVLink hop after the last finalizer of the slowest rank --
+    // in parallel with the row moves, not behind the wait for the last sequence's word (N = 8: the gather of 3072
+    // words behind tail CTA 0's own rows cost ~2 us per step).
+    const bool exchange_cta = p.xchg != nullptr && t == 0;
+    if (p.xchg != nullptr) --t;
+    const int seq = exchange_cta ? 0 : p.B - 1 - t / p.tail_pieces, tp = exchange_cta ? 0 : t % p.tail_pieces;
+    if (!exchange_cta) {
         const int tail_items = (p.seq_items + p.tail_pieces - 1) / p.tail_pieces;
         const int it0 = tp * tail_items;
         const int it_end = it0 + tail_items < p.seq_items ? it0 + tail_items : p.seq_items;
@@ -532,7 +538,7 @@ SD_DEVINL void kv_tail_body(const KvParams& p, const int t, unsigned long long* 
         piece_items_run(p, tag, seq, it0 + (int)threadIdx.x, it_end, word, park, park_items);
     }
     if (trace && threadIdx.x == 0) trace[1] = global_timer_ns();
-    if (p.xchg && t == 0) {
+    if (exchange_cta) {
         // Multi-GPU exchange, served by ONE tail CTA in parallel with the others' stores (not on the closing path).
         // The records arrive progressively (a finalizer pushes right after publishing its word), so the gather
         // starts polling NOW and only the last few words are waited for.  The exchange epoch may advance only when

@@ -1320,7 +1320,7 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
             }
             if (lag > B) lag = B;
             kp.lag = lag;
-            const unsigned n_tail = (unsigned)lag * (unsigned)kp.tail_pieces;
+            const unsigned n_tail = (unsigned)lag * (unsigned)kp.tail_pieces + (kp.xchg ? 1u : 0u);  // (+ the exchange CTA)
             kp.total_ctas = n_tail;
             static const int l2pf = [] {  // A/B (default off: measured no gain, the tail is bandwidth-bound, not latency-bound)
                 const char* e = getenv("SD_B200_STEP_L2_PREFETCH");

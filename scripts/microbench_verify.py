@@ -218,7 +218,7 @@ def write_markdown(path, rows, info):
                     keys.append(k)
         out += [f"## {title}", "", "| " + " | ".join(keys) + " |", "|" + "---|" * len(keys)]
         for r in rs:
-            out.append("| " + " | ".join(str(r.get(k, "")) for k in keys) + " |")
+            out.append("| " + " | ".join(" ".join(str(r.get(k, "")).split()).replace("|", "/") for k in keys) + " |")
         out.append("")
     Path(path).write_text("\n".join(out))
 

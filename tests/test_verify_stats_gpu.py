@@ -78,3 +78,60 @@ def test_temperature_scaling():
     x = O.as_f32(to_np(logits), "bf16") / np.float32(T)
     e_acc, e_prob = O.accept_typical(x[:, :4], to_np(ids), 0.5)
     np.testing.assert_allclose(out["token_prob"].cpu().numpy(), e_prob, rtol=5e-4, atol=ATOL)
+
+
+@pytest.mark.parametrize("mode,threshold", [("typical", 0.3), ("confidence", 0.5), ("topk", 5)])
+def test_opt125m_vocabulary_sampling_mode_with_partial_kv_reuse(mode, threshold):
+    """BASELINE configs[3]: OPT-125M target (V = 50272, 12 layers x 12 heads x 64) + GPT-2 draft with sampling-mode
+    acceptance and partial KV reuse: the softmax-ratio rules evaluated by the fused verify kernel, then kv_append of the
+    accepted rows into the arena and a rollback (shorter lengths) before the next step -- accept lengths exact away from
+    the threshold, KV rows and lengths bit-exact."""
+    from oracle import c_oracle
+    from specdec.cache.kv_arena import KVArena
+    from specdec.verify_step import VerifyStep
+
+    B, K, V, layers, H, D, L, cap = 8, 4, 50272, 12, 12, 64, 9, 96
+    dev = torch.device("cuda")
+    arena = KVArena(layers, B, H, D, cap, K + 1, torch.float16, dev)
+    g = torch.Generator().manual_seed(11)
+    arena.k[:, :, :, :L] = torch.randn(layers, B, H, L, D, generator=g).to(torch.float16).cuda()
+    arena.v[:, :, :, :L] = torch.randn(layers, B, H, L, D, generator=g).to(torch.float16).cuda()
+    arena.set_lengths([L] * B)
+    T = 0.8
+    step = VerifyStep(B, K, V, arena=arena, logits_dtype=torch.float16, device=dev, mode=mode, threshold=threshold, temperature=T)
+    exp_k, exp_v = to_np(arena.k).copy(), to_np(arena.v).copy()
+    lens = np.full(B, L, np.int32)
+    for it in range(4):
+        logits, ids = make_verify_inputs(B, K + 1, K, V, "fp16", p_match=0.7, seed=300 + it, device="cuda")
+        step.logits.copy_(logits)
+        step.draft_ids.copy_(ids)
+        arena.new_k.copy_(torch.randn(arena.new_k.shape, generator=g).to(torch.float16))
+        arena.new_v.copy_(torch.randn(arena.new_v.shape, generator=g).to(torch.float16))
+        step.run()
+        torch.cuda.synchronize()
+        x = O.as_f32(to_np(logits), "fp16") / np.float32(T)
+        if mode == "typical":
+            e_acc, e_stat = O.accept_typical(x[:, :K], to_np(ids), threshold)
+            near = np.abs(e_stat - threshold) < 1e-3
+            np.testing.assert_allclose(step.token_prob.cpu().numpy(), e_stat, rtol=5e-4, atol=1e-6)
+        elif mode == "confidence":
+            e_acc, e_stat = O.accept_confidence(x[:, :K], threshold)
+            near = np.abs(e_stat - threshold) < 1e-3
+        else:
+            e_acc = O.accept_topk(x[:, :K], to_np(ids), int(threshold))
+            near = np.zeros(1, dtype=bool)
+        acc = step.accept_len.cpu().numpy()
+        if not near.any():
+            np.testing.assert_array_equal(acc, e_acc)
+        # the append follows the kernel's own accept lengths: KV bytes and lengths are exact whatever the rule decided
+        nk, nv = to_np(arena.new_k), to_np(arena.new_v)
+        for l in range(layers):
+            new_lens = c_oracle.kv_arena_append(exp_k[l], lens, nk[l], acc + 1, True)
+            c_oracle.kv_arena_append(exp_v[l], lens, nv[l], acc + 1, True)
+        lens = new_lens
+        np.testing.assert_array_equal(arena.seq_lens.cpu().numpy(), lens)
+        np.testing.assert_array_equal(to_np(arena.k), exp_k)
+        np.testing.assert_array_equal(to_np(arena.v), exp_v)
+        # partial KV reuse: roll every second sequence back by one row (a length update; stale rows are overwritten later)
+        lens = lens - (np.arange(B) % 2).astype(np.int32)
+        arena.set_lengths(lens)

@@ -383,3 +383,44 @@ def test_fused_launch_with_finalizer_push_and_one_step_lag(world):
     finally:
         for x in xs:
             x.close()
+
+
+@pytest.mark.parametrize("lag", [0, 5])
+def test_fused_step_with_a_grid_larger_than_residency(lag):
+    """B = 256, V = 128256: 9000+ CTAs against 592 resident ones, so most CTAs a waiting CTA depends on are long gone
+    and the last ones are dispatched late -- the dispatch-order assumption documented in include/sd_verify.h
+    (sd_verify_append) at scale.  Small lag (5 sequences < one wave) makes carrying CTAs really wait.  Results vs the
+    oracle; no bounded wait may have expired."""
+    B, K, V, layers, H, D, L, cap = 256, 4, 128256, 2, 8, 128, 3, 24
+    dev = torch.device("cuda")
+    arena = KVArena(layers, B, H, D, cap, K + 1, torch.bfloat16, dev)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    arena.k[:, :, :, :L] = torch.randn(layers, B, H, L, D, generator=g, device="cuda").to(torch.bfloat16)
+    arena.v[:, :, :, :L] = torch.randn(layers, B, H, L, D, generator=g, device="cuda").to(torch.bfloat16)
+    arena.set_lengths([L] * B)
+    step = VerifyStep(B, K, V, arena=arena, device=dev)
+    cuda_ops.set_fused_mode(0, lag)
+    try:
+        exp_k, exp_v = to_np(arena.k).copy(), to_np(arena.v).copy()
+        lens = np.full(B, L, np.int32)
+        for it in range(3):
+            gl = torch.Generator(device="cuda").manual_seed(40 + it)
+            step.logits.copy_(torch.randn(B, K + 1, V, generator=gl, device="cuda").to(torch.bfloat16))
+            ids = torch.randint(0, V, (B, K), generator=gl, device="cuda")
+            plant = torch.rand(B, K, generator=gl, device="cuda") < 0.75
+            bi, ki = torch.nonzero(plant, as_tuple=True)
+            step.logits[bi, ki, ids[bi, ki]] = 10.0
+            step.draft_ids.copy_(ids)
+            arena.new_k.copy_(torch.randn(arena.new_k.shape, generator=gl, device="cuda").to(torch.bfloat16))
+            arena.new_v.copy_(torch.randn(arena.new_v.shape, generator=gl, device="cuda").to(torch.bfloat16))
+            step.run()
+            torch.cuda.synchronize()
+            acc, mask, tgt, bonus, lens = _oracle_step(exp_k, exp_v, lens, step.logits, step.draft_ids, to_np(arena.new_k), to_np(arena.new_v))
+            np.testing.assert_array_equal(step.accept_len.cpu().numpy(), acc)
+            np.testing.assert_array_equal(step.target_ids.cpu().numpy(), tgt)
+            np.testing.assert_array_equal(arena.seq_lens.cpu().numpy(), lens)
+            np.testing.assert_array_equal(to_np(arena.k), exp_k)
+            np.testing.assert_array_equal(to_np(arena.v), exp_v)
+    finally:
+        cuda_ops.set_fused_mode(0, 0)
+    assert cuda_ops.device_error() == 0
