@@ -267,7 +267,7 @@ SD_DEVINL unsigned exchange_gather_records(const sd_exchange* x, int32_t* out) {
                 SpinGuard guard;
                 while ((unsigned)(w[u] >> 32) != want) {
                     if (!guard.keep_waiting(kSpinPeerWords)) break;
-                    __nanosleep(64);
+                    __nanosleep(200);
                     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w[u]) : "l"(words + i) : "memory");
                 }
                 if (out) out[i] = (int)(unsigned)w[u];

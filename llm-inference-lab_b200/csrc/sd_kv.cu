@@ -243,7 +243,7 @@ int kv_prepare_col(const sd_kv_layer* layers, int n_layers, int B, int H, int R,
     p.fused = 1;
     p.flags = nullptr;
     p.epoch_word = nullptr;
-    p.lag = p.pieces = p.piece_items = p.seq_items = p.tail_pieces = p.eager_rows = p.l2_prefetch = p.uniform = p.stagger_ns = 0;
+    p.lag = p.pieces = p.piece_items = p.seq_items = p.tail_pieces = p.eager_rows = p.l2_prefetch = p.uniform = p.stagger_ns = p.one_warp_wait = 0;
     p.carry_ni = kCarryNI;
     p.ls_arena = p.ls_new = 0;
     p.layer0 = sd_kv_layer{nullptr, nullptr, nullptr, nullptr};
@@ -322,7 +322,7 @@ static int kv_append_impl(const sd_kv_layer* layers, const sd_kv_layer* single, 
     p.fused = 0;
     p.flags = nullptr;
     p.epoch_word = nullptr;
-    p.lag = p.pieces = p.piece_items = p.seq_items = p.tail_pieces = p.eager_rows = p.l2_prefetch = p.uniform = p.stagger_ns = 0;
+    p.lag = p.pieces = p.piece_items = p.seq_items = p.tail_pieces = p.eager_rows = p.l2_prefetch = p.uniform = p.stagger_ns = p.one_warp_wait = 0;
     p.carry_ni = kCarryNI;
     p.ls_arena = p.ls_new = 0;
     p.layer0 = sd_kv_layer{nullptr, nullptr, nullptr, nullptr};

@@ -58,6 +58,7 @@ struct KvParams {
     int64_t ls_arena, ls_new;
     int uniform;
     int carry_ni;               // items a carrying verify CTA parks per thread (1..kCarryNI)
+    int one_warp_wait;          // A/B: one warp polls the chunk's mbarrier, the rest wait in bar.sync
     int stagger_ns;             // A/B: first-wave CTAs delay their bulk copy by slot * stagger_ns
     int l2_prefetch;            // verify CTAs of the last `lag` sequences pull their sequence's rows into L2 (default on)
     int eager_rows;             // A/B: carrying CTAs fetch their rows without looking at the sequence word first
@@ -540,18 +541,20 @@ SD_DEVINL void kv_tail_body(const KvParams& p, int t, unsigned long long* trace,
     if (trace && threadIdx.x == 0) trace[1] = global_timer_ns();
     if (exchange_cta) {
         // Multi-GPU exchange, served by ONE tail CTA in parallel with the others' stores (not on the closing path).
-        // The records arrive progressively (a finalizer pushes right after publishing its word), so the gather
-        // starts polling NOW and only the last few words are waited for.  The exchange epoch may advance only when
-        // every local finalizer has read it: with lag 0 that is implied by the gather itself (it has collected this
-        // rank's own records of the epoch, each tagged by its finalizer); with lag 1 wait for the words.
         if (p.xchg_packed) {  // records pushed from here: the finalizers released them before publishing their words
             wait_all_words(p, tag);
             __syncthreads();
             __threadfence();
             exchange_push_cta(p.xchg, p.xchg_packed, p.B);
         }
+        // Wait for this rank's own finalizers FIRST (local words, cheap to poll): in lock-step the peers' records are then
+        // at most one NVLink hop away, so the record words -- lines that the peers are writing over NVLink -- are polled
+        // for a microsecond, not for the whole second half of the kernel (256 threads hammering them from the moment
+        // this CTA starts measured SLOWER at N = 8: 37.7 us per step against 35.9 us).  It is also what the epoch
+        // advance needs: every local finalizer has read the exchange epoch.
+        wait_all_words(p, tag);
+        __syncthreads();
         const unsigned xepoch = exchange_gather_records(p.xchg, p.xchg_out);
-        if (p.xchg->lag != 0 || p.xchg_packed) wait_all_words(p, tag);
         exchange_advance(p.xchg, xepoch);
     }
     __shared__ int s_last;

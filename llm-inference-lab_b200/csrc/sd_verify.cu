@@ -890,7 +890,15 @@ SD_DEVINL void step_cta_body(const VerifyParams& p, const KvParams& kp, const in
     if (b >= p.B - lag && kp.l2_prefetch) kv_piece_prefetch(kp, b, piece);  // rows of a tail sequence: into L2, now
     ThreadAcc<T, false> acc;
     acc.reset();
-    vbar_wait(bar, 0u);
+    // ONE warp polls the mbarrier; the others block in the hardware barrier behind it.  (256 threads spinning on
+    // try_wait for the ~3.5 us a chunk takes under load cost issue slots that the epilogues of the other resident CTAs
+    // need: ncu showed 55 % of the issue slots busy in a kernel that mostly waits.)
+    if (kp.one_warp_wait) {
+        if (tid < 32) vbar_wait(bar, 0u);
+        __syncthreads();
+    } else {
+        vbar_wait(bar, 0u);
+    }
     const uint4* src = reinterpret_cast<const uint4*>(stage);
 #pragma unroll 4
     for (int k = tid; k < nv; k += nthreads) acc.add(src[k], v0 + k, true, p.scale_log2);
@@ -1332,6 +1340,11 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
                 return e ? atoi(e) : 0;
             }();
             kp.stagger_ns = stagger;
+            static const int oww = [] {
+                const char* e = getenv("SD_B200_STEP_ONE_WARP_WAIT");
+                return e ? atoi(e) : 0;
+            }();
+            kp.one_warp_wait = oww;
             p.words = kp.flags;
             p.epoch_word = kp.epoch_word;
             p.seq_lens = kp.seq_lens_out;

@@ -57,18 +57,29 @@ def test_blackwell_native_instructions_present():
 
 
 @pytest.mark.skipif(not shutil.which(CUOBJDUMP), reason="cuobjdump not installed")
-def test_fused_step_kernel_keeps_four_ctas_per_sm():
-    """The shipped fused step kernel (bf16 logits, 3 rows of K/V in flight per append thread) must stay at
-    <= 64 registers without a stack frame: 256 threads x 64 registers = 4 resident CTAs per SM (the 80-register
-    build of the first captures held 3 and measured 33.5 us per step against 32.6 us)."""
+@pytest.mark.parametrize("kernel", ["verify_step_kernelI13__nv_bfloat16EE", "verify_append_kernelI13__nv_bfloat16Li3EE"],
+                         ids=["lagged_append_default", "round1_layout"])
+def test_fused_step_kernel_keeps_four_ctas_per_sm(kernel):
+    """The shipped fused step kernel (verify_step_kernel<bf16>: lagged append, rows parked in shared memory) and the
+    round-1 layout kept for A/B must stay at <= 64 registers without a stack frame: 256 threads x 64 registers = 4
+    resident CTAs per SM (an 80-register build of round 1 held 3 and measured 33.5 us per step against 32.6 us; three
+    CTAs per SM measured 33.2 us against 31.1 us in round 2)."""
     lib = build.build_cuda_kernels()
     r = subprocess.run([CUOBJDUMP, "--dump-resource-usage", str(lib)], capture_output=True, text=True)
     if r.returncode != 0:
         pytest.skip("cuobjdump could not dump resource usage")
     lines = r.stdout.splitlines()
-    hits = [lines[i + 1] for i, ln in enumerate(lines)
-            if "verify_append_kernelI13__nv_bfloat16Li3EE" in ln and i + 1 < len(lines)]
-    assert hits, "verify_append_kernel<bf16,3> not found in the library"
+    hits = [lines[i + 1] for i, ln in enumerate(lines) if kernel in ln and i + 1 < len(lines)]
+    assert hits, f"{kernel} not found in the library"
     regs = int(re.search(r"REG:(\d+)", hits[0]).group(1))
     stack = int(re.search(r"STACK:(\d+)", hits[0]).group(1))
     assert regs <= 64 and stack == 0, hits[0]
+
+
+@pytest.mark.skipif(not shutil.which(CUOBJDUMP), reason="cuobjdump not installed")
+def test_fused_step_kernel_parks_rows_with_cp_async():
+    """verify_step_kernel<bf16>: one UBLKCP for the logits chunk, LDGSTS (cp.async) for the carried KV rows, packed
+    NaN-propagating max for the fold."""
+    sass = _sass("_ZN2sd18verify_step_kernelI13__nv_bfloat16EEvNS_12VerifyParamsENS_8KvParamsEiii")
+    assert len(re.findall(r"UBLKCP", sass)) == 1
+    assert "LDGSTS" in sass and "HMNMX2.BF16_V2.NAN" in sass
