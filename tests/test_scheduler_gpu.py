@@ -120,3 +120,71 @@ def test_graph_capture_drop_in():
     with pytest.raises(RuntimeError):
         gc.replay()
     assert not GraphCapture(enabled=False).capture_once(fn, x)
+
+
+def test_start_gate_holds_the_stream_until_released():
+    """sd_start_gate, single GPU: work enqueued behind an armed gate does not start before release() (the host's
+    'everything is enqueued' flag), and starts right after."""
+    import time
+
+    from kernels import cuda_ops
+
+    gate = cuda_ops.StartGate("cuda:0")
+    x = torch.zeros(1 << 20, device="cuda")
+    torch.cuda.synchronize()
+    gate.arm(hold=True)
+    x.add_(1.0)
+    done = torch.cuda.Event()
+    done.record()
+    time.sleep(0.05)
+    assert not done.query(), "the gate let the stream through before release()"
+    gate.release()
+    t0 = time.perf_counter()
+    while not done.query():
+        assert time.perf_counter() - t0 < 5.0, "the gate never opened"
+    assert float(x[0]) == 1.0
+    gate.arm(hold=False)  # released before it is enqueued: passes immediately
+    x.add_(1.0)
+    torch.cuda.synchronize()
+    assert float(x[0]) == 2.0 and cuda_ops.device_error() == 0
+
+
+def test_start_gate_rendezvous_of_emulated_ranks():
+    """Two ranks emulated in one process (one exchange buffer each, gates on two streams): neither stream passes its
+    gate before BOTH have arrived and been released; three rounds exercise the gate counter."""
+    import time
+
+    from kernels import cuda_ops
+    from scheduler.batch_shard import PeerExchange
+
+    xs = PeerExchange.emulate(2, 8, 4, "cuda")
+    try:
+        gates = [cuda_ops.StartGate("cuda:0", x) for x in xs]
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        flags = [torch.zeros(1, device="cuda") for _ in range(2)]
+        for rnd in range(3):
+            evs = []
+            with torch.cuda.stream(streams[0]):
+                gates[0].arm(hold=True)
+                flags[0].add_(1.0)
+                evs.append(torch.cuda.Event())
+                evs[0].record()
+            gates[0].release()
+            time.sleep(0.02)
+            assert not evs[0].query(), "rank 0 passed the gate before rank 1 arrived"
+            with torch.cuda.stream(streams[1]):
+                gates[1].arm(hold=True)
+                flags[1].add_(1.0)
+                evs.append(torch.cuda.Event())
+                evs[1].record()
+            time.sleep(0.02)
+            assert not evs[0].query() and not evs[1].query(), "rank 1's host flag is still down"
+            gates[1].release()
+            t0 = time.perf_counter()
+            while not (evs[0].query() and evs[1].query()):
+                assert time.perf_counter() - t0 < 5.0, f"round {rnd}: the gate never opened"
+            assert float(flags[0]) == rnd + 1 and float(flags[1]) == rnd + 1
+        assert cuda_ops.device_error() == 0
+    finally:
+        for x in xs:
+            x.close()
