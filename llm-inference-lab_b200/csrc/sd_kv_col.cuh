@@ -58,6 +58,10 @@ struct KvParams {
     int64_t ls_arena, ls_new;
     int uniform;
     int carry_ni;               // items a carrying verify CTA parks per thread (1..kCarryNI)
+    // verify CTAs of the first `lag` sequences carry nothing: their chunk fills stage + park (upc_big units, S_big per row)
+    int n_big, S_big, upc_big;
+    int fetch;                  // A/B: 0 = chunk by one bulk copy, 1 = by cp.async, 2 = half / half
+    int bulk_split;             // A/B: bytes per bulk copy of a logits chunk (0 = the whole chunk in one copy)
     int one_warp_wait;          // A/B: one warp polls the chunk's mbarrier, the rest wait in bar.sync
     int stagger_ns;             // A/B: first-wave CTAs delay their bulk copy by slot * stagger_ns
     int l2_prefetch;            // verify CTAs of the last `lag` sequences pull their sequence's rows into L2 (default on)
@@ -394,6 +398,7 @@ SD_DEVINL void kv_piece_begin(const KvParams& p, const int seq, const int piece,
             }
         }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // (its own group: the chunk's cp.async part can be waited for alone)
 }
 
 struct PieceKeep {

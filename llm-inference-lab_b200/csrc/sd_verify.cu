@@ -856,25 +856,45 @@ template <typename T>
 SD_DEVINL void step_cta_body(const VerifyParams& p, const KvParams& kp, const int unit, unsigned char* stage, uint64_t* bar,
                              uint4* park) {
     const int tid = threadIdx.x, nthreads = blockDim.x;
-    const int chunk = unit % p.S;
-    const int row = unit / p.S;
+    // Sequences [0, lag) have nothing to carry (no sequence `lag` places before them): their CTAs use the WHOLE shared
+    // memory of the CTA (stage + park) for a bigger logits chunk -- upc_big units, S_big chunks per row.  Throughput here
+    // is bytes in flight / loaded latency (~5.5 us): with 36 KB per CTA the first phase of the launch streamed at
+    // ~3.4 TB/s (21 MB in flight), with stage + park = 52 KB it streams like the carrying phase.
+    const bool big = unit < kp.n_big;
+    const int S = big ? kp.S_big : p.S;
+    const int upc = big ? kp.upc_big : p.units_per_chunk;
+    const int local = big ? unit : unit - kp.n_big;
+    const int lrow = local / S;
+    const int chunk = local - lrow * S;
+    const int row = (big ? 0 : kp.lag * p.rows) + lrow;
     const int b = row / p.rows;
-    const int it0 = chunk * p.units_per_chunk;
-    int it1 = it0 + p.units_per_chunk;
+    const int it0 = chunk * upc;
+    int it1 = it0 + upc;
     if (it1 > p.upr) it1 = p.upr;
     const RowGeom<T> g = row_geom<T>(p, row);
     const int v0 = it0 * nthreads;
     int nv = g.nvec - v0;
     const int cap = (it1 - it0) * nthreads;
     nv = nv < 0 ? 0 : (nv > cap ? cap : nv);
+    // Fetch of the chunk: kp.fetch 0 = ONE bulk copy (TMA), 1 = cp.async by every thread (LSU path), 2 = first half bulk,
+    // second half cp.async.  A bulk copy progresses at ~6.3 GB/s whatever its size (a small window of outstanding requests
+    // per operation: 36 KB in ~6 us, 52 KB in ~8 us), so four of them per SM stream at ~3.5 TB/s; cp.async requests have
+    // no such window.
+    const int nv_bulk = kp.fetch == 0 ? nv : (kp.fetch == 1 ? 0 : ((nv / 2) & ~7));
     if (tid == 0) {
         if (kp.stagger_ns > 0 && unit < 4 * 148) __nanosleep((unsigned)((unit / 148) * kp.stagger_ns));  // A/B: de-synchronise the first wave
-        if (nv > 0) {
-            vbar_arrive_expect_tx(bar, (unsigned)nv * 16u);
-            vbulk_g2s(stage, g.vp + v0, (unsigned)nv * 16u, bar);
+        if (nv_bulk > 0) {
+            vbar_arrive_expect_tx(bar, (unsigned)nv_bulk * 16u);
+            const unsigned total = (unsigned)nv_bulk * 16u, sub = kp.bulk_split > 0 ? (unsigned)kp.bulk_split : total;
+            for (unsigned off = 0; off < total; off += sub)
+                vbulk_g2s(stage + off, reinterpret_cast<const unsigned char*>(g.vp + v0) + off, total - off < sub ? total - off : sub, bar);
         } else {
             vbar_arrive(bar);
         }
+    }
+    if (nv_bulk < nv) {
+        for (int k = nv_bulk + tid; k < nv; k += nthreads) cp_async16(stage + (size_t)k * 16, g.vp + v0 + k);
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     // The launch epoch is CONSUMED here (the branch cannot be resolved before the load returns), i.e. before this
     // CTA publishes anything: the closing CTA advances the epoch only after every partial has been published.
@@ -883,8 +903,8 @@ SD_DEVINL void step_cta_body(const VerifyParams& p, const KvParams& kp, const in
     if (epoch_raw == 0xffffffffu) return;  // (never a valid epoch: the closing CTA skips it)
     const unsigned tag = (epoch_raw + 1u) & 0xffffffu;
     const int lag = kp.lag;
-    const int piece = unit - b * kp.pieces;
-    const bool carries = b >= lag;
+    const int piece = big ? 0 : local - (b - lag) * kp.pieces;
+    const bool carries = !big;
     PieceRegs pr;
     if (carries) kv_piece_begin(kp, b - lag, piece, tag, pr, park);
     if (b >= p.B - lag && kp.l2_prefetch) kv_piece_prefetch(kp, b, piece);  // rows of a tail sequence: into L2, now
@@ -899,12 +919,17 @@ SD_DEVINL void step_cta_body(const VerifyParams& p, const KvParams& kp, const in
     } else {
         vbar_wait(bar, 0u);
     }
+    if (nv_bulk < nv) {  // the cp.async part of the chunk (the carried rows, committed after it, may still be in flight)
+        if (carries) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    }
     const uint4* src = reinterpret_cast<const uint4*>(stage);
 #pragma unroll 4
     for (int k = tid; k < nv; k += nthreads) acc.add(src[k], v0 + k, true, p.scale_log2);
     if (p.trace && tid == 0) p.trace[(size_t)blockIdx.x * 4 + 1] = global_timer_ns();
     if (publish_segment<T, false, false>(p, g, acc, row, it0, it1, chunk, tid, nthreads))
-        finalize_sequence<T, false, false>(p, b, p.S, tid, nthreads, tag);
+        finalize_sequence<T, false, false>(p, b, S, tid, nthreads, tag);
     if (carries) kv_piece_finish(kp, tag, pr, park);
 }
 
@@ -925,8 +950,9 @@ __global__ void __launch_bounds__(256, 4) verify_step_kernel(const VerifyParams 
     if (vp.trace && threadIdx.x == 0) {  // evidence runs (tools/trace_step.py): {entry, scan done / rows stored, exit, SM id}
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const unsigned kind = (int)blockIdx.x < kp.n_big ? 0u : ((int)blockIdx.x < n_verify ? 1u : 2u);  // big verify / carrying verify / tail
         vp.trace[(size_t)blockIdx.x * 4 + 0] = global_timer_ns();
-        vp.trace[(size_t)blockIdx.x * 4 + 3] = smid;
+        vp.trace[(size_t)blockIdx.x * 4 + 3] = smid | (kind << 16);
     }
     if ((int)blockIdx.x < n_verify)
         step_cta_body<T>(vp, kp, (int)blockIdx.x, stage, &bar, reinterpret_cast<uint4*>(stage + stage_bytes));
@@ -1314,13 +1340,15 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
             if (tail_items_env > 0 && tail_items_env < tail_park_items) tail_park_items = tail_items_env;
             kp.tail_pieces = (int)((seq_items + (long long)tail_park_items * threads - 1) / ((long long)tail_park_items * threads));
             if (kp.tail_pieces < 1) kp.tail_pieces = 1;
-            // Lag: far enough that a carrying CTA finds the word of its sequence published when it starts (one
-            // wave of resident CTAs plus the finalizer's latency), i.e. about 1.5 waves' worth of sequences.
+            // Lag: far enough that a carrying CTA finds the word of its sequence published when it starts (one wave of
+            // resident CTAs plus the finalizer's latency: >= 1.5 waves' worth of sequences).  Measured optimum with the
+            // big chunks of the non-carrying sequences: ~2.4 waves (B = 64: lag 34..46 -> 30.6-30.8 us, 26 -> 31.4, 50 ->
+            // 31.3; B = 128: lag 40 -> 51.4 us, 26 -> 53.7, 80 -> 53.0).
             int lag = g_fused_lag;
             if (lag <= 0) {
-                static const int lag_pct = [] {  // A/B: lag as a percentage of one wave of resident CTAs (default 150)
+                static const int lag_pct = [] {  // A/B: lag as a percentage of one wave of resident CTAs
                     const char* e = getenv("SD_B200_STEP_LAG_PCT");
-                    return e ? atoi(e) : 150;
+                    return e ? atoi(e) : 240;
                 }();
                 const long long resident = (long long)step_occupancy(logit_dtype, threads, smem_step) * sm_count();
                 lag = (int)((resident * lag_pct / 100 + kp.pieces - 1) / kp.pieces);
@@ -1328,6 +1356,16 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
             }
             if (lag > B) lag = B;
             kp.lag = lag;
+            // the first `lag` sequences: bigger chunks (stage + park), fewer CTAs
+            static const int big_env = [] {
+                const char* e = getenv("SD_B200_STEP_BIG_CHUNKS");
+                return (e && e[0] == '0') ? 0 : 1;
+            }();
+            kp.upc_big = big_env ? (int)((stage_bytes + (size_t)carry_ni * 2 * 16 * threads) / ((size_t)threads * 16)) : p.units_per_chunk;
+            if (kp.upc_big < p.units_per_chunk) kp.upc_big = p.units_per_chunk;
+            kp.S_big = (upr + kp.upc_big - 1) / kp.upc_big;
+            kp.n_big = lag * rows * kp.S_big;
+            grid = (unsigned)(kp.n_big + (B - lag) * rows * p.S);
             const unsigned n_tail = (unsigned)lag * (unsigned)kp.tail_pieces + (kp.xchg ? 1u : 0u);  // (+ the exchange CTA)
             kp.total_ctas = n_tail;
             static const int l2pf = [] {  // A/B (default off: measured no gain, the tail is bandwidth-bound, not latency-bound)
@@ -1345,6 +1383,16 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
                 return e ? atoi(e) : 0;
             }();
             kp.one_warp_wait = oww;
+            static const int bsplit = [] {
+                const char* e = getenv("SD_B200_STEP_BULK_SPLIT");
+                return e ? atoi(e) : 0;
+            }();
+            kp.bulk_split = bsplit > 0 ? (bsplit + 15) / 16 * 16 : 0;
+            static const int fetch = [] {
+                const char* e = getenv("SD_B200_STEP_FETCH");
+                return e ? atoi(e) : 0;
+            }();
+            kp.fetch = fetch;
             p.words = kp.flags;
             p.epoch_word = kp.epoch_word;
             p.seq_lens = kp.seq_lens_out;

@@ -84,14 +84,16 @@ def main():
         tr = tr[:n_all]
         t0 = tr[:, 0].min()
         start, mid, end = (tr[:, 0] - t0) / 1e3, (tr[:, 1] - t0) / 1e3, (tr[:, 2] - t0) / 1e3
-        upr = ((a.V // 8 + 1) + 255) // 256          # 4 KB units per bf16 row
-        S = (upr + 8) // 9                            # 36 KB chunks (the default of the bulk-chunk verify body)
-        n_verify = a.B * R * S
+        kind = (tr[:, 3] >> 16) & 3                   # 0 big verify (first `lag` sequences), 1 carrying verify, 2 tail
+        n_verify = int((kind < 2).sum())
+        n_big = int((kind == 0).sum())
+        S = 0
         v = slice(0, n_verify)
         t = slice(n_verify, n_all)
-        per_seq_end = end[v].reshape(a.B, -1).max(axis=1)
+        per_seq_end = np.array([end[v].min(), end[v].max()])
         out = {
-            "rep": rep, "ctas": n_all, "verify_ctas": n_verify, "tail_ctas": n_all - n_verify, "S": S,
+            "rep": rep, "ctas": n_all, "verify_ctas": n_verify, "big_chunk_ctas": n_big, "tail_ctas": n_all - n_verify,
+            "big_exit_pct": pct(end[:n_big]) if n_big else [],
             "event_us": round(e0.elapsed_time(e1) * 1e3, 2),
             "first_entry_to_last_exit_us": round(float(end.max()), 2),
             "verify_start_pct": pct(start[v]), "verify_scan_done_pct": pct(mid[v]), "verify_exit_pct": pct(end[v]),
