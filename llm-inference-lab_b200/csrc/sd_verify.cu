@@ -399,10 +399,15 @@ SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int n
     // trips that hide behind the partial poll below) and only used once the record is final
     int x_world = 0, x_width = 0, x_rank = 0, x_rpr = 0;
     unsigned x_epoch = 0u;
+    // fused step: the sequence's length before this step, requested NOW as well (this thread is its only reader and
+    // writer in the launch) -- loaded where it is used, it was one more L2 round trip between "accept_len known" and
+    // "word published", i.e. on the critical path of every consumer of the word and of the launch's tail
+    int len_before = 0;
     if (wid == 0) {
 #pragma unroll
         for (int h = 0; h < 2; ++h)
             if (h * 32 + lane < p.K) my_id[h] = load_id(p.ids, p.id_dtype, (int64_t)b * p.id_stride_b + h * 32 + lane);
+        if (lane == 0 && p.words && p.seq_lens) len_before = p.seq_lens[b];
         if (p.xchg) {
             const sd_exchange* x = p.xchg;
             x_world = x->world;
@@ -522,7 +527,7 @@ SD_DEVINL void finalize_sequence(const VerifyParams& p, const int b, const int n
         // gathering CTA needs to know before it advances that epoch.
         __syncwarp();
         if (lane == 0) {
-            const int len = p.seq_lens ? p.seq_lens[b] : 0;
+            const int len = len_before;
             const int n_keep = nacc + 1;
             int64_t room = p.kv_capacity - len;
             room = room < 0 ? 0 : (room > p.kv_R ? p.kv_R : room);
@@ -907,7 +912,8 @@ SD_DEVINL void step_cta_body(const VerifyParams& p, const KvParams& kp, const in
     const bool carries = !big;
     PieceRegs pr;
     if (carries) kv_piece_begin(kp, b - lag, piece, tag, pr, park);
-    if (b >= p.B - lag && kp.l2_prefetch) kv_piece_prefetch(kp, b, piece);  // rows of a tail sequence: into L2, now
+    if (b >= p.B - lag && kp.l2_prefetch)  // rows of a tail sequence: into L2, now
+        kv_piece_prefetch(kp, b, local - (big ? b : b - lag) * p.rows * S, p.rows * S);
     ThreadAcc<T, false> acc;
     acc.reset();
     // ONE warp polls the mbarrier; the others block in the hardware barrier behind it.  (256 threads spinning on
@@ -1338,6 +1344,7 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
                 return e ? atoi(e) : 0;
             }();
             if (tail_items_env > 0 && tail_items_env < tail_park_items) tail_park_items = tail_items_env;
+            const int tail_park_max = tail_park_items;
             kp.tail_pieces = (int)((seq_items + (long long)tail_park_items * threads - 1) / ((long long)tail_park_items * threads));
             if (kp.tail_pieces < 1) kp.tail_pieces = 1;
             // Lag: far enough that a carrying CTA finds the word of its sequence published when it starts (one wave of
@@ -1356,6 +1363,21 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
             }
             if (lag > B) lag = B;
             kp.lag = lag;
+            // Tail pieces: as many per sequence as keep ALL tail CTAs resident at once (one wave), i.e. the smallest
+            // tail CTAs that still start together -- B = 64: 14 pieces of 5 items per thread (574 CTAs on 592 slots)
+            // 27.85 us per step; 12 pieces of 6 items (what the shared memory holds) 28.2 us; 18 of 4: 28.25 us.
+            if (tail_items_env <= 0) {
+                const long long resident = (long long)step_occupancy(logit_dtype, threads, smem_step) * sm_count();
+                long long tp = resident / lag;
+                if (tp > kp.tail_pieces) {
+                    int items = (int)((seq_items + tp * threads - 1) / (tp * threads));
+                    if (items < 1) items = 1;
+                    if (items < tail_park_max) {
+                        tail_park_items = items;
+                        kp.tail_pieces = (int)((seq_items + (long long)items * threads - 1) / ((long long)items * threads));
+                    }
+                }
+            }
             // the first `lag` sequences: bigger chunks (stage + park), fewer CTAs
             static const int big_env = [] {
                 const char* e = getenv("SD_B200_STEP_BIG_CHUNKS");
@@ -1406,6 +1428,16 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
                 return (e && e[0] == '1') ? 1 : 0;
             }();
             kp.eager_rows = eager;
+            static const int tail_order = [] {
+                const char* e = getenv("SD_B200_STEP_TAIL_ORDER");
+                return e ? atoi(e) : 1;  // measured: 29.1 us per step against 30.0 us with the last sequence first
+            }();
+            kp.tail_order = tail_order;
+            static const int tail_peek = [] {
+                const char* e = getenv("SD_B200_STEP_TAIL_PEEK");
+                return e ? atoi(e) : 0;
+            }();
+            kp.tail_peek = tail_peek;
             if (g_trace && (size_t)(grid + n_tail) <= g_trace_ctas) p.trace = g_trace;
             return to_status(launch_step(p, kp, logit_dtype, grid + n_tail, (int)grid, threads, stage_bytes, smem_step, tail_park_items, st));
         }
