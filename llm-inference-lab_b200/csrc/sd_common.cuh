@@ -244,10 +244,12 @@ SD_DEVINL unsigned exchange_gather_records(const sd_exchange* x, int32_t* out) {
         const unsigned long long* words =
             reinterpret_cast<const unsigned long long*>(own + kExchangeHeaderBytes) + (size_t)(src & 3u) * world * rpr * width;
         const int n = world * rpr * width;
-        // Batches of kU words per thread: all loads of a batch are issued before the first tag check (one L2
-        // round trip per batch instead of one per word -- at world = 8 a thread owns 12 words); a word whose
-        // tag is stale is re-polled on its own.
-        constexpr int kU = 6;
+        // kU words per thread and pass (world = 8: a thread owns 12 words -> ONE pass).  Every poll round re-loads ALL words
+        // of the pass whose tag is still stale, back to back, and only then looks at them: the gather ends one L2 round trip
+        // after the last record has landed.  (Polled one word after the other -- the previous form -- a thread that owned
+        // the records of the last sequences of four ranks needed four serial round trips after the last arrival: the
+        // words a thread owns are 256 apart, so at world = 8 every third one falls into the same part of a rank's batch.)
+        constexpr int kU = 12;
         for (int i0 = threadIdx.x; i0 < n; i0 += blockDim.x * kU) {
             unsigned long long w[kU];
             bool live[kU];
@@ -257,21 +259,24 @@ SD_DEVINL unsigned exchange_gather_records(const sd_exchange* x, int32_t* out) {
                 const int row = i / width;
                 const int r = row / rpr;
                 live[u] = i < n && (row - r * rpr) < base + (r < extra ? 1 : 0);  // not a padding row of an uneven shard
-                w[u] = 0ull;
-                if (live[u]) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w[u]) : "l"(words + i) : "memory");
+                w[u] = 0ull;  // (tag 0 is never wanted: want = epoch + 1 >= 1)
+            }
+            SpinGuard guard;
+            for (;;) {
+#pragma unroll
+                for (int u = 0; u < kU; ++u)
+                    if (live[u] && (unsigned)(w[u] >> 32) != want)
+                        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w[u]) : "l"(words + i0 + u * blockDim.x) : "memory");
+                bool stale = false;
+#pragma unroll
+                for (int u = 0; u < kU; ++u) stale |= live[u] && (unsigned)(w[u] >> 32) != want;
+                if (!stale) break;
+                if (!guard.keep_waiting(kSpinPeerWords)) break;
+                __nanosleep(100);
             }
 #pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                if (!live[u]) continue;
-                const int i = i0 + u * blockDim.x;
-                SpinGuard guard;
-                while ((unsigned)(w[u] >> 32) != want) {
-                    if (!guard.keep_waiting(kSpinPeerWords)) break;
-                    __nanosleep(200);
-                    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w[u]) : "l"(words + i) : "memory");
-                }
-                if (out) out[i] = (int)(unsigned)w[u];
-            }
+            for (int u = 0; u < kU; ++u)
+                if (live[u] && out) out[i0 + u * blockDim.x] = (int)(unsigned)w[u];
         }
     }
     return epoch;

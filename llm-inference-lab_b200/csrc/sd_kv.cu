@@ -244,7 +244,7 @@ int kv_prepare_col(const sd_kv_layer* layers, int n_layers, int B, int H, int R,
     p.flags = nullptr;
     p.epoch_word = nullptr;
     p.lag = p.pieces = p.piece_items = p.seq_items = p.tail_pieces = p.eager_rows = p.l2_prefetch = p.uniform = p.stagger_ns = p.one_warp_wait = 0;
-    p.n_big = p.S_big = p.upc_big = p.bulk_split = p.fetch = p.tail_order = p.tail_peek = 0;
+    p.n_big = p.S_big = p.upc_big = p.bulk_split = p.fetch = p.tail_order = p.tail_peek = p.pf_ahead = p.n_verify = 0;
     p.carry_ni = kCarryNI;
     p.ls_arena = p.ls_new = 0;
     p.layer0 = sd_kv_layer{nullptr, nullptr, nullptr, nullptr};
@@ -324,7 +324,7 @@ static int kv_append_impl(const sd_kv_layer* layers, const sd_kv_layer* single, 
     p.flags = nullptr;
     p.epoch_word = nullptr;
     p.lag = p.pieces = p.piece_items = p.seq_items = p.tail_pieces = p.eager_rows = p.l2_prefetch = p.uniform = p.stagger_ns = p.one_warp_wait = 0;
-    p.n_big = p.S_big = p.upc_big = p.bulk_split = p.fetch = p.tail_order = p.tail_peek = 0;
+    p.n_big = p.S_big = p.upc_big = p.bulk_split = p.fetch = p.tail_order = p.tail_peek = p.pf_ahead = p.n_verify = 0;
     p.carry_ni = kCarryNI;
     p.ls_arena = p.ls_new = 0;
     p.layer0 = sd_kv_layer{nullptr, nullptr, nullptr, nullptr};

@@ -67,6 +67,8 @@ struct KvParams {
     int l2_prefetch;            // verify CTAs of the last `lag` sequences pull their sequence's rows into L2 (default on)
     int eager_rows;             // A/B: carrying CTAs fetch their rows without looking at the sequence word first
     int tail_order;             // tail CTAs: 0 = the LAST sequence's pieces are dispatched first, 1 = the earliest tail sequence's
+    int pf_ahead;               // A/B: verify CTA u prefetches the logits chunk of verify CTA u + pf_ahead into L2 (0 = off)
+    int n_verify;               // verify CTAs of the fused step launch
     int tail_peek;              // tail CTAs look at the sequence word while row 0 is being requested; rows 1.. only if kept
     FastDiv fd_vpr, fd_R, fd_H; // item -> (column, row, head, layer) without integer division
 };

@@ -901,6 +901,28 @@ SD_DEVINL void step_cta_body(const VerifyParams& p, const KvParams& kp, const in
         for (int k = nv_bulk + tid; k < nv; k += nthreads) cp_async16(stage + (size_t)k * 16, g.vp + v0 + k);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    // A/B (kp.pf_ahead): pull the logits chunk of the verify CTA `pf_ahead` places behind this one into L2 with ONE
+    // cp.async.bulk.prefetch.L2 -- bytes in flight towards DRAM that need no shared memory; the CTA that owns the chunk
+    // then copies it from L2.  (The resident CTAs hold 592 x 51 KB = 30 MB in shared memory; at the ~6 us a chunk takes
+    // under load that caps the logits phase at ~5 TB/s.)
+    if (kp.pf_ahead > 0 && tid == 0) {
+        const int unit2 = unit + kp.pf_ahead;
+        if (unit2 < kp.n_verify) {
+            const bool big2 = unit2 < kp.n_big;
+            const int S2 = big2 ? kp.S_big : p.S;
+            const int upc2 = big2 ? kp.upc_big : p.units_per_chunk;
+            const int local2 = big2 ? unit2 : unit2 - kp.n_big;
+            const int lrow2 = local2 / S2;
+            const int chunk2 = local2 - lrow2 * S2;
+            const int row2 = (big2 ? 0 : kp.lag * p.rows) + lrow2;
+            const RowGeom<T> g2 = row_geom<T>(p, row2);
+            const int v02 = chunk2 * upc2 * nthreads;
+            int nv2 = g2.nvec - v02;
+            nv2 = nv2 < 0 ? 0 : (nv2 > upc2 * nthreads ? upc2 * nthreads : nv2);
+            if (nv2 > 0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g2.vp + v02), "r"((unsigned)nv2 * 16u) : "memory");
+        }
+    }
     // The launch epoch is CONSUMED here (the branch cannot be resolved before the load returns), i.e. before this
     // CTA publishes anything: the closing CTA advances the epoch only after every partial has been published.
     unsigned epoch_raw;
@@ -1438,6 +1460,12 @@ static int run_verify(bool stats, const void* logits, int logit_dtype, int64_t s
                 return e ? atoi(e) : 0;
             }();
             kp.tail_peek = tail_peek;
+            static const int pf_ahead = [] {
+                const char* e = getenv("SD_B200_STEP_PF_AHEAD");
+                return e ? atoi(e) : 0;
+            }();
+            kp.pf_ahead = pf_ahead;
+            kp.n_verify = (int)grid;
             if (g_trace && (size_t)(grid + n_tail) <= g_trace_ctas) p.trace = g_trace;
             return to_status(launch_step(p, kp, logit_dtype, grid + n_tail, (int)grid, threads, stage_bytes, smem_step, tail_park_items, st));
         }
