@@ -397,7 +397,8 @@ int sd_kv_set_variant(int variant);
  * workspace sd_verify_attention_workspace_bytes(...) bytes (split-KV partials), no init needed
  * scale    softmax scale (1/sqrt(D) when <= 0)
  * n_splits 0 = heuristic (wave-quantised cost model on max_seq_len_host, bounded by the workspace);
- *          > 1 needs sd_verify_attention_workspace_bytes(..., n_splits) bytes
+ *          > 1 needs sd_verify_attention_workspace_bytes(..., n_splits) bytes;
+ *          SD_ATTN_BALANCED = the persistent form described below (its own, initialised workspace)
  * max_seq_len_host  upper bound of seq_lens known on the host (-1 = derive from kv_stride_h); the split heuristic
  *          uses it -- the kernel reads the true lengths from seq_lens -- and max_seq_len_host + R > capacity is
  *          refused (SD_ERR_CAPACITY)
@@ -410,6 +411,18 @@ int sd_kv_set_variant(int variant);
  * One launch (+ one small merge launch when n_splits > 1).
  */
 size_t sd_verify_attention_workspace_bytes(int B, int Hq, int R, int D, int max_splits);
+
+/* Balanced (persistent) form of kernel 3: n_splits = SD_ATTN_BALANCED.  The grid is exactly the resident CTAs and the
+ * key tiles of all (sequence, KV head) items are cut into equal spans, one per CTA; an item cut by a span boundary is
+ * finished by whichever of its CTAs arrives last (per-item counter; nothing waits).  Same results as the standard
+ * form up to fp32 summation order.  Worth it when B * Hkv is not close to a multiple of the resident CTAs (512 items on
+ * 296 slots).  B <= 512.  The workspace (sd_verify_attention_balanced_workspace_bytes) holds the counters and the
+ * partial slots and must be zeroed ONCE with sd_verify_attention_balanced_workspace_init; every launch leaves the
+ * counters zero again, so it is graph-replayable.  One workspace serves one launch at a time (launches on one stream,
+ * PDL included, are fine); re-initialise it after an aborted launch. */
+#define SD_ATTN_BALANCED (-1)
+size_t sd_verify_attention_balanced_workspace_bytes(int B, int Hq, int Hkv, int R, int D);
+int sd_verify_attention_balanced_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
 int sd_verify_attention(const void* q, const void* k_arena, const void* v_arena,
                         const int32_t* seq_lens, void* out, void* workspace,
                         size_t workspace_bytes, int dtype, int B, int Hq, int Hkv, int R, int D,

@@ -61,6 +61,8 @@ SIGNATURES = {
     "sd_sample_set_fast_path": (_i, [_i]),
     "sd_sample_bonus": (_i, [_vp, _i, _i64, _i64, _vp, _i, _i, _vp, _f, _i, _f, _vp, _vp, _i, _i, _i, _vp]),
     "sd_verify_attention_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "sd_verify_attention_balanced_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "sd_verify_attention_balanced_workspace_init": (_i, [_vp, _sz, _vp]),
     "sd_verify_attention_set_tuning": (_i, [_i]),
     "sd_verify_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i64, _i64,
                                  _i64, _i64, _vp, _f, _i, _vp]),

@@ -576,6 +576,33 @@ def verify_append_launch(
 
 
 # ------------------------------------------------------------------------------------------ attention
+ATTN_BALANCED = -1  # SD_ATTN_BALANCED (include/sd_verify.h)
+
+
+class BalancedAttentionWorkspace:
+    """Workspace of the balanced (persistent) form of the verify attention: per-item tile counters + per-CTA partial
+    slots, zeroed ONCE here (every launch leaves the counters zero again -> graph-replayable).  One workspace serves one
+    launch at a time: keep one per stream / per captured graph node chain.  ``reset()`` after an aborted launch."""
+
+    def __init__(self, B: int, Hq: int, Hkv: int, R: int, D: int, device: torch.device):
+        lib = _capi.lib()
+        self.shape = (B, Hq, Hkv, R, D)
+        self.device = torch.device(device)
+        self.buf = torch.empty(int(lib.sd_verify_attention_balanced_workspace_bytes(B, Hq, Hkv, R, D)), dtype=torch.uint8,
+                               device=self.device)
+        self.reset()
+
+    def reset(self) -> None:
+        lib = _capi.lib()
+        with torch.cuda.device(self.device):
+            lib.check(lib.sd_verify_attention_balanced_workspace_init(self.buf.data_ptr(), self.buf.numel(),
+                                                                      _stream_ptr(self.device)),
+                      "sd_verify_attention_balanced_workspace_init")
+
+    def fits(self, B: int, Hq: int, Hkv: int, R: int, D: int) -> bool:
+        return (B, Hq, Hkv, R, D) == self.shape
+
+
 def verify_attention_cuda(
     q: torch.Tensor,
     k_arena: torch.Tensor,
@@ -587,8 +614,12 @@ def verify_attention_cuda(
     out: Optional[torch.Tensor] = None,
     workspace: Optional[torch.Tensor] = None,
     overflow: Optional[torch.Tensor] = None,
+    balanced: Optional[BalancedAttentionWorkspace] = None,
 ) -> torch.Tensor:
     """(K+1)-query causal decode attention over the KV arena (new registry op ``verify_attention``).
+
+    ``balanced``: a :class:`BalancedAttentionWorkspace` selects the persistent form (one CTA per resident slot, equal
+    spans of key tiles; B <= 512) -- same results up to fp32 summation order.
 
     q [B,Hq,R,D]; k_arena/v_arena [B,Hkv,C,D] with the R new rows already appended at
     seq_lens[b]..; seq_lens [B] int32 = rows valid before them.  Replaces K sequential SDPA decode
@@ -609,7 +640,10 @@ def verify_attention_cuda(
         out = torch.empty_like(q)
     lib = _capi.lib()
     es = q.element_size()
-    if workspace is None:
+    if balanced is not None:
+        assert balanced.fits(B, Hq, Hkv, R, D), f"balanced workspace was made for {balanced.shape}"
+        workspace, n_splits = balanced.buf, ATTN_BALANCED
+    elif workspace is None:
         need = int(lib.sd_verify_attention_workspace_bytes(B, Hq, R, D, n_splits))
         workspace = _scratch.attn_workspace(q.device, need)
     with torch.cuda.device(q.device):

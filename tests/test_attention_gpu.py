@@ -161,6 +161,93 @@ def test_full_size_against_torch_fp32():
     _check(out[idx], want64, "full size vs oracle")
 
 
+# ---- balanced (persistent) form: one CTA per resident slot, equal spans of key tiles, last arriver finishes a cut item ----
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("shape", SHAPES, ids=[s[0] for s in SHAPES])
+def test_balanced_against_oracle(shape, dtype):
+    """Small shapes: fewer tiles than CTAs, so every tile is its own segment and an item is put together from as many
+    partials as it has tiles -- the fix-up path carries the whole result."""
+    _, B, Hq, Hkv, R, D, lens, cap = shape
+    q, k, v, sl = _case(B, Hq, Hkv, R, D, lens, cap, dtype)
+    ws = cuda_ops.BalancedAttentionWorkspace(B, Hq, Hkv, R, D, "cuda")
+    want = _oracle(q, k, v, sl)
+    for rep in range(3):  # the counters must be left zero by every launch
+        out = cuda_ops.verify_attention_cuda(q.cuda(), k.cuda(), v.cuda(), sl.cuda(), max_seq_len=max(lens), balanced=ws)
+        _check(out, want, f"{shape[0]} balanced, launch {rep}")
+    assert int(ws.buf[:256].view(torch.int32).abs().sum()) == 0, "tile counters not reset"  # (the first 64 items' counters)
+
+
+@pytest.mark.parametrize("geom", [(24, 8, 128), (32, 8, 64), (12, 12, 64)], ids=["llama3b", "llama1b", "gpt2"])
+@pytest.mark.parametrize("ragged", [False, True], ids=["equal", "ragged"])
+def test_balanced_full_size_equals_standard_form(geom, ragged):
+    """BASELINE configs[2] / configs[3] geometries at B=64, L<=1024: spans of ~57 tiles cut most items once.  Against the
+    standard form (same tiles, same per-tile arithmetic; only the fp32 merge order of a cut item differs) and the torch
+    fp32 reference.  Replayed from a CUDA graph as well."""
+    Hq, Hkv, D = geom
+    B, R, L = 64, 5, 1024
+    cap = L + R
+    g = torch.Generator(device="cuda").manual_seed(77)
+    q = torch.randn(B, Hq, R, D, generator=g, device="cuda").to(torch.bfloat16)
+    k = torch.randn(B, Hkv, cap, D, generator=g, device="cuda").to(torch.bfloat16)
+    v = torch.randn(B, Hkv, cap, D, generator=g, device="cuda").to(torch.bfloat16)
+    if ragged:
+        sl = torch.randint(0, L + 1, (B,), generator=torch.Generator().manual_seed(5), dtype=torch.int32).cuda()
+        sl[0], sl[1], sl[B - 1] = 0, L, 3
+    else:
+        sl = torch.full((B,), L, dtype=torch.int32, device="cuda")
+    ws = cuda_ops.BalancedAttentionWorkspace(B, Hq, Hkv, R, D, "cuda")
+    std = cuda_ops.verify_attention_cuda(q, k, v, sl, max_seq_len=L, n_splits=1)
+    bal = cuda_ops.verify_attention_cuda(q, k, v, sl, max_seq_len=L, balanced=ws)
+    # one bf16 ulp (2^-7 relative) where the fp32 merge order of a cut item flips the final rounding
+    excess = ((bal.float() - std.float()).abs() - (1e-3 + 2.0 ** -7 * std.float().abs())).max().item()
+    assert excess <= 0, f"balanced vs standard form: {excess} beyond one bf16 ulp"
+    mask = torch.arange(cap, device="cuda")[None, None, :] <= (sl.long()[:, None, None] + torch.arange(R, device="cuda")[None, :, None])
+    kk = k.float().repeat_interleave(Hq // Hkv, dim=1)
+    vv = v.float().repeat_interleave(Hq // Hkv, dim=1)
+    with torch.nn.attention.sdpa_kernel(torch.nn.attention.SDPBackend.MATH):
+        want = torch.nn.functional.scaled_dot_product_attention(q.float(), kk, vv, attn_mask=mask[:, None])
+    _check(bal, want.cpu().numpy(), "balanced full size")
+    # graph replay: three replays on the same workspace, every one complete and identical
+    out = torch.empty_like(q)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        cuda_ops.verify_attention_cuda(q, k, v, sl, max_seq_len=L, balanced=ws, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(2):
+            cuda_ops.verify_attention_cuda(q, k, v, sl, max_seq_len=L, balanced=ws, out=out)
+    for _ in range(3):
+        out.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, bal), "graph replay of the balanced form differs from the eager launch"
+
+
+def test_balanced_clamp_and_errors():
+    B, Hq, Hkv, R, D, cap = 3, 8, 4, 5, 64, 40
+    q, k, v, _ = _case(B, Hq, Hkv, R, D, [cap - R] * B, cap, "bf16", seed=3, poison=False)
+    lens_ok = torch.tensor([cap - R, 7, cap - R], dtype=torch.int32)
+    lens_bad = torch.tensor([cap - R, 7, cap + 9], dtype=torch.int32)
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ws = cuda_ops.BalancedAttentionWorkspace(B, Hq, Hkv, R, D, "cuda")
+    want = cuda_ops.verify_attention_cuda(q.cuda(), k.cuda(), v.cuda(), lens_ok.cuda(), overflow=flag, balanced=ws)
+    assert int(flag) == 0
+    _check(want, _oracle(q, k, v, lens_ok), "balanced at capacity")
+    got = cuda_ops.verify_attention_cuda(q.cuda(), k.cuda(), v.cuda(), lens_bad.cuda(), overflow=flag, balanced=ws)
+    assert int(flag) == 1 and torch.equal(got, want)
+    with pytest.raises(AssertionError):  # a workspace made for another shape
+        cuda_ops.verify_attention_cuda(q.cuda()[:2], k.cuda()[:2], v.cuda()[:2], lens_ok.cuda()[:2], balanced=ws)
+    lib = cuda_ops._capi.lib()
+    small = torch.zeros(512, dtype=torch.uint8, device="cuda")
+    qc, kc, vc, lc = q.cuda(), k.cuda(), v.cuda(), lens_ok.cuda()
+    rc = lib.sd_verify_attention(qc.data_ptr(), kc.data_ptr(), vc.data_ptr(), lc.data_ptr(), want.data_ptr(), small.data_ptr(),
+                                 small.numel(), cuda_ops._DTYPE[torch.bfloat16], B, Hq, Hkv, R, D, Hkv * cap * D * 2,
+                                 cap * D * 2, -1, cap, None, 0.0, cuda_ops.ATTN_BALANCED, None)
+    assert rc != 0, "a workspace that cannot hold the partial slots must be refused"
+
+
 def test_lengths_are_clamped_to_the_arena_capacity():
     """a sequence can sit AT capacity (the append kernels clamp there); attention must then neither read
     the next head's rows nor run off the allocation, and must say so."""
