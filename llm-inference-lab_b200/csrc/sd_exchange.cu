@@ -12,6 +12,35 @@ __global__ void __launch_bounds__(256) exchange_wait_kernel(const sd_exchange* x
     exchange_gather_cta(x, out);
 }
 
+// Bounded wait of the start gate.  Unlike the waits inside the step kernels (microseconds; they almost never reach a
+// second look at the clock) a gate legitimately waits for as long as the slowest host needs, so its guard has to survive a
+// step of %globaltimer: on the first gate launch after the GPU had idled for seconds (the CPU-side oracle check of the
+// B = 256 test before it) two reads 40 us apart differed by more than the whole 2 s budget, the plain SpinGuard gave up
+// and the gate opened 78 us after the host's release with no peer present (gpurun_out -> profiles/r2j_gate_probe.md).
+// This guard restarts its window when the clock runs backwards and needs the budget to be exceeded TWICE, each time
+// measured from a fresh reading, before it records the error -- one step of the clock costs nothing, a dead peer is
+// still reported after 2 x kSpinBudgetNs.
+struct GateSpinGuard {
+    unsigned long long t0 = 0ull;
+    unsigned polls = 0u;
+    unsigned strikes = 0u;
+    SD_DEVINL bool keep_waiting(unsigned site) {
+        if ((++polls & 127u) != 0u) return true;
+        const unsigned long long now = global_timer_ns();
+        if (t0 == 0ull || now < t0) {
+            t0 = now;
+            return true;
+        }
+        if (now - t0 < kSpinBudgetNs) return true;
+        if (++strikes < 2u) {
+            t0 = now;
+            return true;
+        }
+        atomicOr(&g_spin_error, site);
+        return false;
+    }
+};
+
 // Start gate (sd_start_gate): one warp.  (1) wait until the HOST has raised *host_go to go_value -- the caller sets it
 // after everything behind the gate has been enqueued, so no rank's GPU outruns its own launch queue; (2) tell every
 // peer "rank r has arrived at gate g" with one 8-byte store into its header, wait for every peer's word; (3) advance
@@ -23,7 +52,7 @@ __global__ void __launch_bounds__(32) start_gate_kernel(const sd_exchange* x, co
     pdl_trigger();
     const int lane = threadIdx.x;
     if (host_go && lane == 0) {
-        SpinGuard guard;
+        GateSpinGuard guard;
         for (;;) {
             unsigned v;
             asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(host_go) : "memory");
@@ -44,7 +73,7 @@ __global__ void __launch_bounds__(32) start_gate_kernel(const sd_exchange* x, co
     }
     for (int r = lane; r < x->world; r += 32) {
         const unsigned long long* src = reinterpret_cast<const unsigned long long*>(own + 64 + 8 * r);
-        SpinGuard guard;
+        GateSpinGuard guard;
         for (;;) {
             unsigned long long v;
             asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");

@@ -2,6 +2,8 @@
 """Per-CTA timeline of the fused step kernel (verify_step_kernel, lagged append) from %globaltimer stamps.
 
     python tools/trace_step.py [--B 64] [--K 4] [--V 128256] [--lag 0] [--layers 28]
+    torchrun --nproc-per-node N tools/trace_step.py --exchange [--xlag 1]   (the step with the peer-memory exchange;
+                                                        --loopback on one GPU = the exchange against the GPU itself)
 
 Prints, relative to the first CTA's entry: when the verify CTAs start / finish their scan / exit, when the tail
 CTAs start / store / exit, and what is left after the last logits byte has been reduced (the tail of the launch).
@@ -37,8 +39,24 @@ def main():
     ap.add_argument("--lag", type=int, default=0)
     ap.add_argument("--nbuf", type=int, default=4)
     ap.add_argument("--reps", type=int, default=6)
+    ap.add_argument("--exchange", action="store_true", help="under torchrun: PeerExchange between the ranks (lock-step at --xlag 0)")
+    ap.add_argument("--loopback", action="store_true", help="one GPU: exchange records with the GPU itself")
+    ap.add_argument("--xlag", type=int, default=0, help="0 = a step gathers its own records, 1 = the previous step's")
     a = ap.parse_args()
-    dev = torch.device("cuda")
+    import os
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    peer = None
+    if a.exchange and world > 1:
+        import torch.distributed as dist
+        from scheduler.batch_shard import BatchShard, PeerExchange
+        dist.init_process_group("nccl", device_id=dev)
+        peer = PeerExchange(BatchShard(a.B * world, world, rank), a.K, dev, lag=a.xlag)
+    elif a.loopback:
+        from scheduler.batch_shard import PeerExchange
+        peer = PeerExchange.emulate(1, a.B, a.K, dev, lag=a.xlag)[0]
+    torch.manual_seed(1234 + rank)
     R = a.K + 1
     if a.lag:
         cuda_ops.set_fused_mode(0, a.lag)
@@ -63,7 +81,7 @@ def main():
         st = steps[i]
         arena.use_staging(tables[i][1], tables[i][2], tables[i][0])
         cuda_ops.verify_append_launch(st.logits, st.draft_ids, st.accept_len, st.accepted_mask, st.target_ids, st.bonus,
-                                      st.packed, st.workspace, st.seq_ready, arena)
+                                      st.packed, st.workspace, st.seq_ready, arena, exchange=peer)
 
     for i in range(a.nbuf):
         run(i)
@@ -74,6 +92,14 @@ def main():
         buf.zero_()
         _capi.lib().sd_verify_set_trace(buf.data_ptr(), cap)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if peer is not None and world > 1:
+            # three untraced steps first: the lock-step exchange itself brings the ranks within a few us of each other
+            _capi.lib().sd_verify_set_trace(None, 0)
+            dist.barrier()
+            torch.cuda.synchronize()
+            for w in range(3):
+                run((rep + 1 + w) % a.nbuf)
+            _capi.lib().sd_verify_set_trace(buf.data_ptr(), cap)
         e0.record()
         run(rep % a.nbuf)
         e1.record()
@@ -92,6 +118,9 @@ def main():
         t = slice(n_verify, n_all)
         per_seq_end = np.array([end[v].min(), end[v].max()])
         out = {
+            "rank": rank, "world": world, "exchange": None if peer is None else ("loopback" if world == 1 else f"peer lag {a.xlag}"),
+            # with an exchange the first tail CTA carries no rows: it gathers the records and advances the exchange epoch
+            "first_tail_cta_start_mid_exit_us": [round(float(x[n_verify]), 2) for x in (start, mid, end)] if n_all > n_verify else [],
             "rep": rep, "ctas": n_all, "verify_ctas": n_verify, "big_chunk_ctas": n_big, "tail_ctas": n_all - n_verify,
             "big_exit_pct": pct(end[:n_big]) if n_big else [],
             "event_us": round(e0.elapsed_time(e1) * 1e3, 2),
