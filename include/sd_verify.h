@@ -133,6 +133,12 @@ int sd_exchange_wait(const sd_exchange* exchange, int32_t* out, void* stream);
  * gather.  Collective over the ranks of the exchange; waits are bounded (sd_device_error, site 16).  No reference
  * counterpart (single GPU). */
 int sd_start_gate(const sd_exchange* exchange, const void* host_go, unsigned go_value, void* stream);
+/* Host-side self-test of the start gate's bounded-wait rule (no GPU): feeds `readings` (successive %globaltimer values,
+ * ns, as the gate sees them every 128 polls) through the same inline function the kernel uses and returns the index of
+ * the reading at which the gate gives up, -1 if it keeps waiting through all of them, -2 on a bad argument.  The rule:
+ * the window restarts on a backwards clock and the budget must be exceeded twice, each time from a fresh reading, so
+ * one step of the clock (seen on the first launch after seconds of GPU idle) opens nothing. */
+int sd_selftest_gate_clock(const unsigned long long* readings, int n, unsigned long long budget_ns);
 
 /* ------------------------------------------------------------------------------------------
  * Kernel 1: fused verify.

@@ -20,22 +20,31 @@ __global__ void __launch_bounds__(256) exchange_wait_kernel(const sd_exchange* x
 // This guard restarts its window when the clock runs backwards and needs the budget to be exceeded TWICE, each time
 // measured from a fresh reading, before it records the error -- one step of the clock costs nothing, a dead peer is
 // still reported after 2 x kSpinBudgetNs.
-struct GateSpinGuard {
+struct GateClockWindow {
     unsigned long long t0 = 0ull;
-    unsigned polls = 0u;
     unsigned strikes = 0u;
+};
+// One look at the clock: true = keep waiting, false = give up.  Host-callable so that the rule is tested on the CPU
+// (sd_selftest_gate_clock, tests/test_capi_symbols.py).
+__host__ __device__ __forceinline__ bool gate_clock_step(GateClockWindow& w, const unsigned long long now,
+                                                         const unsigned long long budget_ns) {
+    if (w.t0 == 0ull || now < w.t0) {
+        w.t0 = now;
+        return true;
+    }
+    if (now - w.t0 < budget_ns) return true;
+    if (++w.strikes < 2u) {
+        w.t0 = now;
+        return true;
+    }
+    return false;
+}
+struct GateSpinGuard {
+    GateClockWindow w;
+    unsigned polls = 0u;
     SD_DEVINL bool keep_waiting(unsigned site) {
         if ((++polls & 127u) != 0u) return true;
-        const unsigned long long now = global_timer_ns();
-        if (t0 == 0ull || now < t0) {
-            t0 = now;
-            return true;
-        }
-        if (now - t0 < kSpinBudgetNs) return true;
-        if (++strikes < 2u) {
-            t0 = now;
-            return true;
-        }
+        if (gate_clock_step(w, global_timer_ns(), kSpinBudgetNs)) return true;
         atomicOr(&g_spin_error, site);
         return false;
     }
@@ -137,6 +146,14 @@ int sd_start_gate(const sd_exchange* exchange, const void* host_go, unsigned go_
     if (!exchange && !host_go) return SD_OK;
     return sd::to_status(sd::launch_kernel(sd::start_gate_kernel, dim3(1), dim3(32), 0, reinterpret_cast<cudaStream_t>(stream),
                                            exchange, reinterpret_cast<const unsigned*>(host_go), go_value));
+}
+
+int sd_selftest_gate_clock(const unsigned long long* readings, int n, unsigned long long budget_ns) {
+    if (!readings || n < 0) return -2;
+    sd::GateClockWindow w;
+    for (int i = 0; i < n; ++i)
+        if (!sd::gate_clock_step(w, readings[i], budget_ns)) return i;
+    return -1;
 }
 
 int sd_exchange_wait(const sd_exchange* exchange, int32_t* out, void* stream) {

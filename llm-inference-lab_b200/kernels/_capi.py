@@ -50,6 +50,7 @@ SIGNATURES = {
     "sd_exchange_free": (_i, [_vp]),
     "sd_exchange_wait": (_i, [_vp, _vp, _vp]),
     "sd_start_gate": (_i, [_vp, _vp, C.c_uint, _vp]),
+    "sd_selftest_gate_clock": (_i, [_vp, _i, C.c_uint64]),
     "sd_verify_set_tuning": (_i, [_i, _i]),
     "sd_verify_set_variant": (_i, [_i, _i]),
     "sd_verify_set_trace": (_i, [_vp, _sz]),

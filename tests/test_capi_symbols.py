@@ -50,6 +50,36 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc == -6
 
 
+def test_start_gate_clock_rule_on_the_host():
+    """The start gate's bounded wait (csrc/sd_exchange.cu: gate_clock_step, the same inline function on host and
+    device): a single step of the clock -- forwards by more than the budget, or backwards -- must not open the gate
+    (profiles/r2j_gate_probe.md); a wait that really outlasts the budget twice over must."""
+    import ctypes as C
+
+    lib = _capi.lib()
+    budget = 2_000_000_000
+    base = 1_760_000_000_000_000_000  # %globaltimer counts ns since the epoch
+
+    def gives_up_at(readings):
+        arr = (C.c_uint64 * len(readings))(*readings)
+        return lib.sd_selftest_gate_clock(arr, len(readings), budget)
+
+    us = 1000
+    steady = [base + i * 40 * us for i in range(1000)]
+    assert gives_up_at(steady) == -1
+    # what the probe saw: the first reading lags by seconds, the following ones are consistent
+    assert gives_up_at([base - 5 * budget] + steady) == -1
+    # a backwards step, then steady
+    assert gives_up_at([base + 10 * budget] + steady) == -1
+    # one forward step in the middle of a long wait
+    assert gives_up_at(steady[:500] + [t + 3 * budget for t in steady[500:]]) == -1
+    # a dead peer: readings 0.5 s apart -> gives up once the budget has been exceeded twice (t0 at reading 0, first
+    # strike at reading 4 = 2 s later, second strike at reading 8)
+    dead = [base + i * (budget // 4) for i in range(40)]
+    assert gives_up_at(dead) == 8
+    assert gives_up_at([]) == -1 and lib.sd_selftest_gate_clock(None, 3, budget) == -2
+
+
 def test_sass_is_sm100a_and_uses_128bit_loads_and_tma():
     """cuobjdump evidence checked here so a wrong -gencode is caught on CPU."""
     out = subprocess.run(["cuobjdump", "-lelf", str(build.LIB_PATH)], capture_output=True, text=True)
