@@ -37,4 +37,7 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope="session")
 def golden_dir():
-    return ROOT / "tests" / "golden"
+    import os
+
+    # SD_GOLDEN_DIR: vectors regenerated from the live reference with another seed (tests/test_oracle_live_reference.py)
+    return Path(os.environ.get("SD_GOLDEN_DIR", ROOT / "tests" / "golden"))

@@ -30,7 +30,7 @@ import numpy as np
 import torch
 
 REF = Path(os.environ.get("SD_REFERENCE_ROOT", "/root/reference"))
-OUT = Path(__file__).resolve().parent
+OUT = Path(os.environ.get("SD_GOLDEN_OUT", Path(__file__).resolve().parent))  # (tests/test_oracle_live_reference.py: a tmp dir)
 sys.path[:0] = [str(REF / "src"), str(REF)]
 
 import kernels.reference as ref_k  # noqa: E402
@@ -44,7 +44,7 @@ from specdec.policies.policies import (  # noqa: E402
     TypicalAcceptancePolicy,
 )
 
-SEED = 1234
+SEED = int(os.environ.get("SD_GOLDEN_SEED", "1234"))  # committed fixtures: 1234
 
 
 def bits(t: torch.Tensor) -> np.ndarray:

@@ -231,7 +231,11 @@ def test_bonus_sampler_distribution_matches_reference(golden_dir):
         for u in (0.0, 0.37, 0.999999):
             tok, _ = O.sample_bonus(row, T, k, p, u)
             assert np.isfinite(x[tok]), (name, u)
-    assert n_exact >= 26
+    # committed fixtures (seed 1234): 26 of 28 rows have no tie across the nucleus boundary; vectors regenerated with
+    # another seed (SD_GOLDEN_DIR, tests/test_oracle_live_reference.py) may have a few more tied rows
+    import os
+
+    assert n_exact >= (26 if "SD_GOLDEN_DIR" not in os.environ else len(z["__cases__"]) - 8)
 
 
 def test_bf16_roundtrip_helper():

@@ -165,3 +165,24 @@ def test_reference_shape_errors_are_assertion_errors(ref):
         ref.verify_prefix_ref(x[0], torch.zeros(2, 3, dtype=torch.long))
     with pytest.raises(AssertionError):
         O.verify_prefix(x[0].numpy(), np.zeros((2, 3), np.int64), "fp32")
+
+
+def test_oracle_pinned_to_vectors_regenerated_with_a_fresh_seed(tmp_path):
+    """Everything tests/golden/make_golden.py records -- verify, kv_append, realign, the four policies, the bonus
+    sampler's distribution -- regenerated from the live reference with ANOTHER seed into a scratch directory, and the
+    whole of tests/test_oracle.py run against those vectors: the oracle is pinned to the reference, not to one set of
+    committed numbers.  (Subprocesses: the reference's packages share their names with this repo's drop-ins.)"""
+    import subprocess
+    import sys
+
+    root = Path(__file__).resolve().parent.parent
+    env = dict(os.environ, SD_GOLDEN_OUT=str(tmp_path), SD_GOLDEN_SEED="4321")
+    gen = subprocess.run([sys.executable, str(root / "tests" / "golden" / "make_golden.py")], env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert gen.returncode == 0, gen.stderr[-2000:]
+    assert {p.name for p in tmp_path.glob("*.npz")} >= {"verify.npz", "kv_append.npz", "kv_realign.npz", "policies.npz", "sampler.npz"}
+    env = dict(os.environ, SD_GOLDEN_DIR=str(tmp_path))
+    run = subprocess.run([sys.executable, "-m", "pytest", str(root / "tests" / "test_oracle.py"), "-q", "-x", "-p", "no:cacheprovider"],
+                         env=env, capture_output=True, text=True, timeout=600, cwd=str(root))
+    assert run.returncode == 0, run.stdout[-3000:]
+    assert " passed" in run.stdout and "failed" not in run.stdout
