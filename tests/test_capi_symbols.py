@@ -50,6 +50,45 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc == -6
 
 
+def test_attention_and_sampler_argument_errors_without_a_gpu():
+    """Host-known argument errors of kernels 3 and 4 and of the per-layer append are rejected before any CUDA call
+    (include/sd_verify.h: sd_status), so they can be pinned here: fake, suitably aligned, never dereferenced pointers."""
+    lib = _capi.lib()
+    P, BF16, F32 = 0x10000, _capi.DTYPE_BF16, 0  # SD_F32 = 0
+
+    def attn(q=P, k=P, v=P, lens=P, out=P, dtype=BF16, B=2, Hq=8, Hkv=2, R=5, D=128, sb=2 * 64 * 256, sh=64 * 256,
+             max_len=-1, cap=0, splits=0):
+        return lib.sd_verify_attention(q, k, v, lens, out, None, 0, dtype, B, Hq, Hkv, R, D, sb, sh, max_len, cap, None,
+                                       0.0, splits, None)
+
+    assert attn(Hq=0) == -1 and attn(R=0) == -1 and attn(B=-1) == -1 and attn(splits=-7) == -1
+    assert attn(Hq=7, Hkv=2) == -2                       # query heads must be a multiple of KV heads
+    assert attn(dtype=F32) == -5 and attn(D=96) == -5    # f16 / bf16, head_dim 64 or 128 only
+    assert attn(B=0) == 0                                # an empty batch is a no-op
+    assert attn(q=None) == -1 and attn(lens=None) == -1
+    assert attn(k=P + 8) == -4 and attn(sh=64 * 256 + 2) == -4 and attn(q=P + 4) == -4
+    assert attn(sh=4 * 256, R=5) == -6                   # 4 rows between two heads < R offered rows
+    assert attn(max_len=60, R=5) == -6                   # host-known length + R beyond the 64-row capacity
+    assert attn(cap=1000) == -6                          # stated capacity does not fit the head stride
+
+    def sample(logits=P, out=P, dtype=BF16, uniform=None, T=1.0, row_index=None, row=0, B=4, rows=5, V=1000):
+        return lib.sd_sample_bonus(logits, dtype, rows * V, V, row_index, 0, row, uniform, T, 0, 1.0, out, None, B, rows, V, None)
+
+    assert sample(rows=0) == -1 and sample(V=0) == -1 and sample(B=-1) == -1
+    assert sample(B=0) == 0
+    assert sample(logits=None) == -1 and sample(out=None) == -1 and sample(dtype=9) == -1
+    assert sample(uniform=P, T=0.0) == -1                # sampling needs a positive temperature (pipeline.py:91-92)
+    assert sample(row=5) == -2 and sample(row=-1) == -2  # constant row outside [0, rows)
+
+    # per-layer append: null arenas / rows, negative base length
+    def layer(ak=P, av=P, nk=P, nv=P, R=4, base_len=0):
+        return lib.sd_kv_append_layer(ak, av, nk, nv, 1, 1, R, 256, 64, 64 * 256, 64 * 256, R * 256, R * 256, 256, base_len,
+                                      None, 0, None, 0, P, None)
+
+    assert layer(ak=None) == -1 and layer(nk=None) == -1 and layer(base_len=-1) == -1
+    assert layer(base_len=62) == -6                      # 62 + 4 rows beyond the 64-row capacity
+
+
 def test_start_gate_clock_rule_on_the_host():
     """The start gate's bounded wait (csrc/sd_exchange.cu: gate_clock_step, the same inline function on host and
     device): a single step of the clock -- forwards by more than the budget, or backwards -- must not open the gate
