@@ -89,6 +89,41 @@ def test_attention_and_sampler_argument_errors_without_a_gpu():
     assert layer(base_len=62) == -6                      # 62 + 4 rows beyond the 64-row capacity
 
 
+def test_fused_step_argument_errors_without_a_gpu():
+    """sd_verify_append (the whole step in one launch): the checks on host-known fields of sd_step_args."""
+    import ctypes as C
+
+    lib = _capi.lib()
+    P = 0x10000
+
+    def args(**kw):
+        a = _capi.StepArgs()
+        a.logits, a.logit_dtype, a.id_dtype = P, _capi.DTYPE_BF16, _capi.ID_I64
+        a.B, a.rows, a.K, a.V = 4, 5, 4, 1000
+        a.stride_b, a.stride_r, a.id_stride_b = 5 * 1000, 1000, 4
+        a.draft_ids = a.accept_len = a.accepted_mask = a.target_ids = a.bonus = a.packed = a.workspace = P
+        a.workspace_bytes = 1 << 20
+        a.layers, a.n_layers, a.H, a.zero_rejected = P, 2, 2, 1
+        a.row_bytes, a.capacity = 256, 64
+        a.arena_stride_b, a.arena_stride_h = 2 * 64 * 256, 64 * 256
+        a.new_stride_b, a.new_stride_h, a.new_stride_r = 2 * 5 * 256, 5 * 256, 256
+        a.max_seq_len_host = -1
+        a.seq_lens = a.ticket = a.step_state = P
+        for k, v in kw.items():
+            setattr(a, k, v)
+        return a
+
+    call = lambda a: lib.sd_verify_append(C.byref(a), None)
+    assert lib.sd_verify_append(None, None) == -1
+    assert call(args(rows=4)) == -2                       # the step needs the K + 1 rows of the teacher-forced pass
+    assert call(args(accept_len=None)) == -1 and call(args(ticket=None)) == -1
+    assert call(args(step_state=None)) == -1 and call(args(step_state=P + 4)) == -1   # 8-byte sequence words
+    assert call(args(exchange=P, packed=None)) == -1      # an exchange needs the packed records
+    assert call(args(B=0)) == 0                           # an empty batch is a no-op
+    assert call(args(max_seq_len_host=60)) == -6          # 60 + 5 offered rows beyond the 64-row capacity
+    assert lib.sd_step_state_bytes(64) == 64 * 8 + 8 and lib.sd_step_state_bytes(0) == 8
+
+
 def test_start_gate_clock_rule_on_the_host():
     """The start gate's bounded wait (csrc/sd_exchange.cu: gate_clock_step, the same inline function on host and
     device): a single step of the clock -- forwards by more than the budget, or backwards -- must not open the gate
