@@ -75,6 +75,17 @@ struct SpinGuard {
             return true;
         }
         if (now - t0 < kSpinBudgetNs) return true;
+#ifdef SD_SPIN_TWO_STRIKE
+        // Default-off (-DSD_SPIN_TWO_STRIKE): the start gate's rule (sd_exchange.cu, GateSpinGuard) for every wait -- one
+        // step of %globaltimer re-arms the window instead of failing the launch; the strike lives in the top bit of
+        // `polls` (no register).  Compiles to the same register counts; not measured on a GPU yet,
+        // so the shipped kernels are built without it.
+        if (!(polls >> 31)) {
+            polls |= 0x80000000u;
+            t0 = now;
+            return true;
+        }
+#endif
         atomicOr(&g_spin_error, site);
         return false;
     }
