@@ -659,6 +659,7 @@ def verify_attention_cuda(
 
 # ------------------------------------------------------------------------------------------ torch ops
 _TORCH_LIB = None
+_TORCH_OP_KERNELS: list = []  # the Python kernels behind the ops defined below (tests call them directly)
 
 
 def _register_torch_ops() -> None:
@@ -682,6 +683,16 @@ def _register_torch_ops() -> None:
         "verify_attention(Tensor q, Tensor k_arena, Tensor v_arena, Tensor seq_lens, float scale, int max_seq_len)"
         " -> Tensor"
     )
+
+    lib.define(
+        "sample_bonus(Tensor logits, Tensor? row_index, Tensor? uniform, float temperature, int top_k, float top_p)"
+        " -> Tensor"
+    )
+
+    def _sample_bonus_op(logits, row_index, uniform, temperature, top_k, top_p):
+        # top_k <= 0 / top_p >= 1 = filter off (reference defaults: pipeline.py:52-53); uniform None = greedy branch
+        return sample_bonus_cuda(logits, row_index=row_index, uniform=uniform, temperature=float(temperature),
+                                 top_k=int(top_k) if top_k > 0 else None, top_p=float(top_p) if top_p < 1.0 else None)
 
     def _verify_step_op(logits, draft_ids, mode, threshold, temperature):
         name = {v: k for k, v in ACCEPT_MODES.items()}[int(mode)]
@@ -720,6 +731,8 @@ def _register_torch_ops() -> None:
     lib.impl("kv_append", _kv_append_op, "CUDA")
     lib.impl("kv_append_with_mask", _kv_append_mask_op, "CUDA")
     lib.impl("verify_attention", _attn_op, "CUDA")
+    lib.impl("sample_bonus", _sample_bonus_op, "CUDA")
+    _TORCH_OP_KERNELS[:] = [_verify_step_op, _kv_append_op, _kv_append_mask_op, _attn_op, _sample_bonus_op]
     _TORCH_LIB = lib
 
 

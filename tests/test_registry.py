@@ -83,6 +83,54 @@ def test_no_cpu_fallback_is_registered():
         kv(torch.zeros(1, 1, 2, 4), torch.zeros(1, 1, 2, 4), torch.zeros(1, 1, 1, 4), torch.zeros(1, 1, 1, 4))
 
 
+def test_torch_custom_ops_are_registered_for_cuda_only():
+    """Every entry point is a ``sd_b200::`` torch custom op with a CUDA kernel and nothing else: the schemas exist and a
+    CPU tensor gets NotImplementedError from the dispatcher (there is no CPU kernel to fall back to)."""
+    ops = torch.ops.sd_b200
+    for name in ("verify_prefix", "verify_prefix_bonus", "verify_step", "kv_append", "kv_append_with_mask",
+                 "kv_append_rows_", "verify_attention", "sample_bonus"):
+        op = getattr(ops, name)
+        assert op.default._schema.name == f"sd_b200::{name}"
+        assert torch._C._dispatch_has_kernel_for_dispatch_key(f"sd_b200::{name}", "CUDA"), name
+        assert not torch._C._dispatch_has_kernel_for_dispatch_key(f"sd_b200::{name}", "CPU"), name
+    assert str(ops.sample_bonus.default._schema) == (
+        "sd_b200::sample_bonus(Tensor logits, Tensor? row_index, Tensor? uniform, float temperature, int top_k, "
+        "float top_p) -> Tensor")
+    with pytest.raises(NotImplementedError):
+        ops.sample_bonus(torch.zeros(2, 3, 16), None, None, 1.0, 0, 1.0)
+    with pytest.raises(NotImplementedError):
+        ops.kv_append(torch.zeros(1, 1, 2, 4), torch.zeros(1, 1, 2, 4), torch.zeros(1, 1, 1, 4), torch.zeros(1, 1, 1, 4))
+    with pytest.raises(NotImplementedError):
+        ops.verify_step(torch.zeros(1, 3, 8), torch.zeros(1, 2, dtype=torch.long), 0, 0.0, 1.0)
+
+
+def test_sample_bonus_op_forwards_the_reference_defaults(monkeypatch):
+    """The op's Python kernel is argument plumbing only: top_k <= 0 and top_p >= 1 switch the filters off
+    (reference defaults, pipeline.py:52-53), a missing ``uniform`` is the greedy branch."""
+    from kernels import cuda_ops
+
+    seen = {}
+
+    def fake(logits, row_index=None, uniform=None, temperature=1.0, top_k=None, top_p=None, **kw):
+        seen.update(row_index=row_index, uniform=uniform, temperature=temperature, top_k=top_k, top_p=top_p, extra=kw)
+        return torch.zeros(logits.shape[0], dtype=torch.int32)
+
+    monkeypatch.setattr(cuda_ops, "sample_bonus_cuda", fake)
+    impl = cuda_ops._TORCH_LIB  # registered at import
+    assert impl is not None
+    # call the registered Python kernel directly (the dispatcher would refuse CPU tensors)
+    kernel = [fn for fn in _registered_python_kernels(cuda_ops) if fn.__name__ == "_sample_bonus_op"][0]
+    x, u = torch.zeros(2, 3, 16), torch.rand(2)
+    kernel(x, None, None, 1.0, 0, 1.0)
+    assert seen["top_k"] is None and seen["top_p"] is None and seen["uniform"] is None and not seen["extra"]
+    kernel(x, torch.tensor([1, 2], dtype=torch.int32), u, 0.7, 50, 0.9)
+    assert seen["top_k"] == 50 and abs(seen["top_p"] - 0.9) < 1e-12 and seen["uniform"] is u and seen["temperature"] == 0.7
+
+
+def _registered_python_kernels(cuda_ops):
+    return list(getattr(cuda_ops, "_TORCH_OP_KERNELS", []))
+
+
 def test_shape_errors_match_reference_before_device_checks():
     fn = kernels.registry.get_best("verify_prefix", "cuda")
     with pytest.raises(AssertionError):
